@@ -1,0 +1,256 @@
+#!/usr/bin/env python
+"""bench.py — the reference's headline metric on its own config, measured on B200.
+
+metric : tokens/s, fwd+bwd (+ grad all-reduce + optimizer step), whole job over N GPUs
+workload (N=1, BASELINE.json configs[1]): RWKV-x070 0.1B (L12 C768 H12) + SigLIP-B/16 @224 -> 196 patches
+         -> AdaptiveAvgPool to 576 image tokens, ctx 2048, batch 8 per GPU, bf16, synthetic data,
+         reference init (zero-init tensors re-randomised).
+Multi-GPU: pure data parallelism, one process per GPU (torchrun), weak scaling (batch 8 per GPU), one
+         bucketed bf16 gradient all-reduce per step over NCCL.
+
+One JSON line on rank 0 (see the task contract): value (inputs resident in HBM), e2e (pinned-host
+inputs copied H2D and the loss read back D2H inside the timed region, through the public
+VisualRWKV.training_step API), roofline of the dominant hand-written kernel (WKV7 backward; the forward
+is reported next to it) timed live with CUDA events on the launching stream, cpu_baseline (the oracle
+port on the host cores, bounded sample), clocks.
+
+`--impl reference` times the reference's own CPU implementation of the path — the oracle port, since
+the reference has no CPU path for x070 and its model.py cannot be imported without
+CUDA/Lightning/DeepSpeed/timm — on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WKV_FWD_BYTES_PER_ELEM = 14  # 6 bf16 reads + 1 bf16 write
+WKV_BWD_BYTES_PER_ELEM = 26  # 7 bf16 reads + 6 bf16 writes
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained"), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port) — shared by cpu_baseline and --impl reference
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps: int, warmup: int, T: int = 256, B: int = 1, n_img_tok: int = 64):
+    """fp32 restatement of the same model (0.1B + SigLIP-B/16@224) on the host cores, fwd+bwd, on a bounded
+    sample: B x T tokens with n_img_tok image tokens (196 patches pooled to n_img_tok)."""
+    from oracle import model_ref as MR
+    from visualrwkv_b200.model import VisualRWKV, default_args, randomize_zero_init
+    ncores = os.cpu_count() or 1
+    torch.set_num_threads(ncores)
+    os.environ.setdefault("OMP_NUM_THREADS", str(ncores))
+    torch.manual_seed(0)
+    args = default_args(num_token_per_image=n_img_tok, ctx_len=T)
+    model = VisualRWKV(args)
+    randomize_zero_init(model)
+    P = {}
+    for k, v in model.state_dict().items():
+        t = v.detach().float().clone()
+        if not k.startswith("vit.") and "emb.weight" not in k:
+            t.requires_grad_(True)
+        P[k] = t
+    cfg = {"vit": model.vit.cfg, "num_token_per_image": n_img_tok, "n_layer": args.n_layer, "n_head": args.dim_att // 64}
+    batch = MR.make_batch(B, T, n_img_tok, 224, seed=1)
+    wkv = MR.oracle_wkv("f32")
+
+    def step():
+        for t in P.values():
+            t.grad = None
+        logits, targets = MR.visual_forward(P, batch, cfg, wkv)
+        loss = MR.training_loss(logits, targets)
+        loss.backward()
+        return float(loss)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    try:
+        import cpuinfo  # py_cpuinfo
+        cpu_name = cpuinfo.get_cpu_info().get("brand_raw", "unknown")
+    except Exception:
+        cpu_name = "unknown"
+    return {"value": B * T / dt, "unit": "tokens/s", "cores": ncores, "kind": "port", "cpu": cpu_name,
+            "sample": f"fwd+bwd of the same 0.1B+SigLIP-B/16 model, fp32, B={B} T={T} ({n_img_tok} image tokens), "
+                      f"{steps} steps after {warmup} warm-up, torch CPU + C oracle WKV7 (OpenMP)",
+            "ms_per_step": dt * 1e3}
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="per-GPU batch (config: 8)")
+    ap.add_argument("--ctx", type=int, default=2048)
+    ap.add_argument("--layers", type=int, default=12)
+    ap.add_argument("--embd", type=int, default=768)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grad-cp", type=int, default=0)
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    config = {"workload": "RWKV-x070 0.1B (L12 C768 H12 N64) + SigLIP-B/16@224 (196 patches -> AdaptiveAvgPool -> 576 image tokens), "
+                          "ctx 2048, batch 8/GPU, fwd+bwd+allreduce+AdamW",
+              "global_batch": a.batch * world, "seq_len": a.ctx, "image_tokens": 576, "parallelism": f"dp{world}",
+              "l2": "working set per step (>2 GB of activations) exceeds the 126 MB L2; no explicit flush"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_run(a.steps, a.warmup)
+        line = {"impl": "reference", "metric": "tokens/s fwd+bwd (T=2048, 576 img-tok)", "value": r["value"], "unit": "tokens/s",
+                "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config, "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu")},
+                "e2e": {"value": r["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    assert torch.cuda.is_available(), "bench.py (impl ours) needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from oracle import model_ref as MR  # synthetic batch generator only (test infrastructure, not timed math)
+    from visualrwkv_b200 import _lib, wkv7
+    from visualrwkv_b200.benchutil import ClockSampler
+    from visualrwkv_b200.ddp import GradBucketReducer
+    from visualrwkv_b200.model import VisualRWKV, default_args, randomize_zero_init
+    _lib.load_torch_ops()
+
+    torch.manual_seed(1234)
+    args = default_args(n_layer=a.layers, n_embd=a.embd, dim_att=a.embd, ctx_len=a.ctx, grad_cp=a.grad_cp)
+    model = VisualRWKV(args)
+    randomize_zero_init(model)
+    model = model.to(device=dev, dtype=torch.bfloat16)
+    model.freeze_emb()  # v7.00/train.py:196: emb is always frozen
+    trainable = [p for p in model.parameters() if p.requires_grad]
+    reducer = GradBucketReducer(trainable) if world > 1 else None
+    # bf16 params + fp32 master/Adam state (what DeepSpeed bf16 keeps), fused AdamW
+    master = [p.detach().float().clone() for p in trainable]
+    for mp in master:
+        mp.grad = torch.zeros_like(mp)
+    opt = torch.optim.AdamW(master, lr=1e-5, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.0, fused=True)
+
+    B, T = a.batch, a.ctx
+    host = MR.make_batch(B, T, 576, 224, seed=100 + rank, img_dtype=torch.bfloat16)
+    host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
+    resident = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
+
+    def train_step(batch):
+        if reducer is not None:
+            reducer.reset()
+        else:
+            for p in trainable:
+                p.grad = None
+        loss = model.training_step(batch)
+        loss.backward()
+        if reducer is not None:
+            reducer.finish()
+        torch._foreach_copy_([m.grad for m in master], [p.grad for p in trainable])
+        opt.step()
+        torch._foreach_copy_(trainable, master)
+        return loss
+
+    def e2e_step():
+        batch = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
+        loss = train_step(batch)
+        return float(loss)  # D2H read of the loss (synchronises)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    for _ in range(max(a.warmup, 3)):
+        train_step(resident)
+    wkv7.PROFILE = []
+    lc0 = wkv7.launch_count()
+    with ClockSampler(local_rank) as cs:
+        ms = timed(lambda: train_step(resident), a.steps)
+    launches = wkv7.launch_count() - lc0
+    prof, wkv7.PROFILE = wkv7.PROFILE, None
+    torch.cuda.synchronize()
+    ms_e2e = timed(e2e_step, a.steps)
+
+    tokens = B * T * world
+    value = tokens / (ms / 1e3)
+    line = {"metric": "tokens/s fwd+bwd (T=2048, 576 img-tok)", "value": value, "unit": "tokens/s", "n_gpus": world,
+            "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+            "e2e": {"value": tokens / (ms_e2e / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": launches, "tokens_per_s_per_gpu": value / world, "clocks": cs.summary()}
+
+    if rank == 0:
+        peaks = load_peaks()
+        nel = B * T * args.n_embd
+        fwd = [e0.elapsed_time(e1) for kind, e0, e1 in prof if kind == "fwd"]
+        bwd = [e0.elapsed_time(e1) for kind, e0, e1 in prof if kind == "bwd"]
+        if fwd and bwd:
+            fms, bms = sum(fwd) / len(fwd), sum(bwd) / len(bwd)
+            peak = peaks["hbm_gbs"]
+            line["roofline"] = {"kernel": "wkv7_bwd_kernel", "bound": "hbm", "achieved": WKV_BWD_BYTES_PER_ELEM * nel / bms / 1e6,
+                                "peak": peak, "unit": "GB/s", "frac": WKV_BWD_BYTES_PER_ELEM * nel / bms / 1e6 / peak,
+                                "traffic": None, "avg_launch_ms": bms, "launches_timed": len(bwd),
+                                "peak_source": peaks["source"], "share_of_step": sum(bwd) / a.steps / ms}
+            line["roofline_wkv7_fwd"] = {"kernel": "wkv7_fwd_kernel", "bound": "hbm", "achieved": WKV_FWD_BYTES_PER_ELEM * nel / fms / 1e6,
+                                         "peak": peak, "unit": "GB/s", "frac": WKV_FWD_BYTES_PER_ELEM * nel / fms / 1e6 / peak,
+                                         "traffic": None, "avg_launch_ms": fms, "launches_timed": len(fwd),
+                                         "share_of_step": sum(fwd) / a.steps / ms}
+        # model FLOPs (GEMMs only): fwd 281 MFLOP/token at 0.1B -> x3 for fwd+bwd
+        C, L, V = args.n_embd, args.n_layer, args.vocab_size
+        lora = 64 + 64 + 32 + 128 if C == 768 else 0
+        per_tok = L * (8 * C * C + 4 * C * lora + 16 * C * C) + 2 * C * V
+        line["gemm_tflops_achieved"] = 3 * per_tok * B * T / (ms / 1e3) / 1e12
+        line["gemm_frac_of_bf16_peak"] = line["gemm_tflops_achieved"] / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"])
+        if world == 1 and not a.no_cpu_baseline:
+            r = cpu_reference_run(steps=2, warmup=1)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,133 @@
+// wkv7_host.cu — C-ABI entry points for the WKV7 recurrence (see include/vrwkv_b200.h).
+// Replaces cuda_forward / cuda_backward of VisualRWKV-v7/v7.00/cuda/wkv7_cuda.cu:132-138.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include <cudaTypedefs.h>
+
+#include "../../include/vrwkv_b200.h"
+#include "host_util.h"
+#include "wkv7_bwd.cuh"
+#include "wkv7_fwd.cuh"
+
+using namespace vrwkv;
+
+static std::atomic<int> g_fwd_variant{0}, g_bwd_variant{0};
+
+extern "C" int vrwkv_wkv7_set_variant(int fwd_variant, int bwd_variant) {
+    g_fwd_variant.store(fwd_variant);
+    g_bwd_variant.store(bwd_variant);
+    return VRWKV_OK;
+}
+
+// [B*T, H*64] matrix of `elem_bytes`-wide elements, box = [16 rows x 64 cols].
+static int make_stream_map(CUtensorMap* m, const void* base, int B, int T, int H, int elem_bytes) {
+    return vrwkv_encode_2d(m, base, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                           elem_bytes, (uint64_t)H * WKV_N, (uint64_t)B * T, (uint64_t)H * WKV_N * elem_bytes, WKV_N,
+                           WKV_TC, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
+template <int L, int R, int NCONV, int NSTAGE>
+static int launch_fwd(const CUtensorMap* tm, const Wkv7FwdArgs& a, cudaStream_t st) {
+    auto kern = wkv7_fwd_kernel<L, R, NCONV, NSTAGE>;
+    const size_t smem = sizeof(Wkv7FwdSmem<NSTAGE>) + 128;
+    static std::atomic<bool> configured{false};
+    if (!configured.load()) {
+        VRWKV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured.store(true);
+    }
+    dim3 grid(a.H, a.B), block((WKV_N / R) * L + NCONV * 32);
+    kern<<<grid, block, smem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], a);
+    VRWKV_CUDA(cudaGetLastError());
+    vrwkv_count_launch(1);
+    return VRWKV_OK;
+}
+
+template <int L, int NCONV, int NSTAGE>
+static int launch_bwd(const CUtensorMap* tm, const Wkv7BwdArgs& a, cudaStream_t st) {
+    auto kern = wkv7_bwd_kernel<L, NCONV, NSTAGE>;
+    const size_t smem = sizeof(Wkv7BwdSmem<NSTAGE>) + 128;
+    static std::atomic<bool> configured{false};
+    if (!configured.load()) {
+        VRWKV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured.store(true);
+    }
+    dim3 grid(a.H, a.B), block(WKV_N * L + NCONV * 32);
+    kern<<<grid, block, smem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], tm[7], a);
+    VRWKV_CUDA(cudaGetLastError());
+    vrwkv_count_launch(1);
+    return VRWKV_OK;
+}
+
+static int check_common(int B, int T, int H, const void* const* ptrs, int nptr) {
+    if (B <= 0 || T <= 0 || H <= 0) return vrwkv_fail(VRWKV_EINVAL, "wkv7: B,T,H must be positive (got %d,%d,%d)", B, T, H);
+    if ((long long)B * T >= (1ll << 31)) return vrwkv_fail(VRWKV_EUNSUP, "wkv7: B*T too large");
+    for (int i = 0; i < nptr; i++) {
+        if (!ptrs[i]) return vrwkv_fail(VRWKV_EINVAL, "wkv7: null pointer (arg %d)", i);
+        if (((uintptr_t)ptrs[i]) & 15) return vrwkv_fail(VRWKV_EINVAL, "wkv7: pointer %d not 16-byte aligned", i);
+    }
+    return VRWKV_OK;
+}
+
+extern "C" int vrwkv_wkv7_forward_state(int B, int T, int H, const uint16_t* w, const uint16_t* q, const uint16_t* k,
+                                        const uint16_t* v, const uint16_t* a, const uint16_t* b, uint16_t* y, float* s,
+                                        float* sa, const float* state_in, float* state_out, void* stream) {
+    const void* ptrs[] = {w, q, k, v, a, b, y};
+    int rc = check_common(B, T, H, ptrs, 7);
+    if (rc) return rc;
+    if (s && (T % WKV_TC) != 0)
+        return vrwkv_fail(VRWKV_EINVAL, "wkv7 forward: T=%d must be a multiple of %d when checkpoints are requested", T, WKV_TC);
+    if ((((uintptr_t)s) | ((uintptr_t)sa) | ((uintptr_t)state_in) | ((uintptr_t)state_out)) & 15)
+        return vrwkv_fail(VRWKV_EINVAL, "wkv7 forward: s/sa/state pointers must be 16-byte aligned");
+    CUtensorMap tm[6];
+    const void* in[6] = {w, q, k, v, a, b};
+    for (int i = 0; i < 6; i++)
+        if ((rc = make_stream_map(&tm[i], in[i], B, T, H, 2))) return rc;
+    Wkv7FwdArgs args{B, T, H, y, s, sa, state_in, state_out};
+    cudaStream_t st = (cudaStream_t)stream;
+    int var = g_fwd_variant.load();
+    if (var == 0) var = 5;
+    switch (var) {
+        case 1: return launch_fwd<4, 2, 4, 4>(tm, args, st);
+        case 2: return launch_fwd<2, 1, 4, 4>(tm, args, st);
+        case 3: return launch_fwd<4, 1, 4, 4>(tm, args, st);
+        case 4: return launch_fwd<8, 1, 4, 4>(tm, args, st);
+        case 5: return launch_fwd<8, 2, 4, 4>(tm, args, st);
+        default: return vrwkv_fail(VRWKV_EINVAL, "wkv7 forward: unknown variant %d", var);
+    }
+}
+
+extern "C" int vrwkv_wkv7_forward(int B, int T, int H, const uint16_t* w, const uint16_t* q, const uint16_t* k,
+                                  const uint16_t* v, const uint16_t* a, const uint16_t* b, uint16_t* y, float* s,
+                                  float* sa, void* stream) {
+    if (!s || !sa) return vrwkv_fail(VRWKV_EINVAL, "wkv7 forward: s and sa are required (model.py:53-54)");
+    if (T % WKV_TC) return vrwkv_fail(VRWKV_EINVAL, "wkv7 forward: T=%d must be a multiple of %d (model.py:49)", T, WKV_TC);
+    return vrwkv_wkv7_forward_state(B, T, H, w, q, k, v, a, b, y, s, sa, nullptr, nullptr, stream);
+}
+
+extern "C" int vrwkv_wkv7_backward(int B, int T, int H, const uint16_t* w, const uint16_t* q, const uint16_t* k,
+                                   const uint16_t* v, const uint16_t* a, const uint16_t* b, const uint16_t* dy,
+                                   const float* s, const float* sa, uint16_t* dw, uint16_t* dq, uint16_t* dk,
+                                   uint16_t* dv, uint16_t* da, uint16_t* db, void* stream) {
+    const void* ptrs[] = {w, q, k, v, a, b, dy, s, sa, dw, dq, dk, dv, da, db};
+    int rc = check_common(B, T, H, ptrs, 15);
+    if (rc) return rc;
+    if (T % WKV_TC) return vrwkv_fail(VRWKV_EINVAL, "wkv7 backward: T=%d must be a multiple of %d (wkv7_cuda.cu:136)", T, WKV_TC);
+    CUtensorMap tm[8];
+    const void* in[7] = {w, q, k, v, a, b, dy};
+    for (int i = 0; i < 7; i++)
+        if ((rc = make_stream_map(&tm[i], in[i], B, T, H, 2))) return rc;
+    if ((rc = make_stream_map(&tm[7], sa, B, T, H, 4))) return rc;
+    Wkv7BwdArgs args{B, T, H, s, dw, dq, dk, dv, da, db};
+    cudaStream_t st = (cudaStream_t)stream;
+    int var = g_bwd_variant.load();
+    if (var == 0) var = 2;
+    switch (var) {
+        case 1: return launch_bwd<4, 4, 3>(tm, args, st);
+        case 2: return launch_bwd<2, 4, 3>(tm, args, st);
+        case 3: return launch_bwd<8, 4, 3>(tm, args, st);
+        default: return vrwkv_fail(VRWKV_EINVAL, "wkv7 backward: unknown variant %d", var);
+    }
+}

@@ -1,0 +1,89 @@
+"""Data-parallel gradient exchange: one process per GPU, a bucketed all-reduce of the
+gradients over NCCL (NVLink 5 / NVSwitch) launched from autograd hooks so it overlaps the backward of
+earlier layers.  Replaces what DeepSpeed ZeRO-1 does implicitly for the reference
+(v7.00/train.py:55,214-216: reduce-scatter + all-gather in 200 MB buckets).
+
+Gradients live as views into flat per-bucket buffers (no gather/scatter copies); a bucket is reduced
+as soon as the last of its parameters has accumulated its gradient.  The path shards over the batch
+only; there is no other collective on the data path (loss logging gathers one scalar per rank,
+v7.00/src/model.py:436-440).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+class GradBucketReducer:
+    def __init__(self, params, bucket_bytes: int = 32 << 20, process_group=None):
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.params = [p for p in params if p.requires_grad]
+        # backward produces gradients roughly in reverse registration order
+        order = list(reversed(self.params))
+        self.buckets = []  # (flat, [params])
+        cur, cur_bytes = [], 0
+        for p in order:
+            nb = p.numel() * p.element_size()
+            if cur and (cur_bytes + nb > bucket_bytes or p.dtype != cur[0].dtype or p.device != cur[0].device):
+                self._close(cur)
+                cur, cur_bytes = [], 0
+            cur.append(p)
+            cur_bytes += nb
+        if cur:
+            self._close(cur)
+        self._pending = [0] * len(self.buckets)
+        self._handles = []
+        self._bucket_of = {}
+        for bi, (_, ps) in enumerate(self.buckets):
+            for p in ps:
+                self._bucket_of[p] = bi
+                p.register_post_accumulate_grad_hook(self._hook)
+        self.reset()
+
+    def _close(self, ps):
+        n = sum(p.numel() for p in ps)
+        flat = torch.zeros(n, dtype=ps[0].dtype, device=ps[0].device)
+        off = 0
+        for p in ps:
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.buckets.append((flat, ps))
+
+    def reset(self):
+        """Call once per step before backward: zero the flat gradient buffers (grads are views)."""
+        for bi, (flat, ps) in enumerate(self.buckets):
+            flat.zero_()
+            self._pending[bi] = len(ps)
+        self._handles = []
+
+    def _hook(self, p):
+        bi = self._bucket_of[p]
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0 and self.world > 1:
+            flat = self.buckets[bi][0]
+            if dist.get_backend(self.pg) == "nccl":
+                h = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.pg, async_op=True)
+                self._handles.append((h, None))
+            else:  # gloo (CPU tests): SUM then scale
+                h = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+                self._handles.append((h, flat))
+
+    def finish(self):
+        """Call after backward, before the optimizer: waits for every in-flight bucket."""
+        if self.world > 1:
+            # parameters that received no gradient this step still have to be reduced
+            for bi, n in enumerate(self._pending):
+                if n > 0:
+                    flat = self.buckets[bi][0]
+                    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
+                    flat.div_(self.world)
+                    self._pending[bi] = 0
+        for h, flat in self._handles:
+            h.wait()
+            if flat is not None:
+                flat.div_(self.world)
+        self._handles = []
+
+    def grad_bytes(self) -> int:
+        return sum(f.numel() * f.element_size() for f, _ in self.buckets)

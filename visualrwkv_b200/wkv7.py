@@ -1,0 +1,101 @@
+"""WKV7 operator surface — mirrors VisualRWKV-v7/v7.00/src/model.py:45-70.
+
+`WindBackstepping` / `RUN_CUDA_RWKV7g` keep the reference's names, argument order, assertions and
+saved-tensor contract, and call the same `torch.ops.wind_backstepping.{forward,backward}` ops —
+which here are implemented by the sm_100a kernels of csrc/wkv7_{fwd,bwd}.cuh through the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+from . import _lib
+
+HEAD_SIZE = int(os.environ.get("RWKV_HEAD_SIZE_A", "64"))  # env contract of model.py:40
+CHUNK_LEN = 16                                              # model.py:41
+assert HEAD_SIZE == 64, "the sm_100a WKV7 kernels are built for head size 64 (model.py:69 hard-wires it)"
+
+
+# bench.py sets PROFILE = [] to collect (kind, start_event, end_event) per launch on the current stream
+PROFILE = None
+
+
+def _timed(kind, fn):
+    if PROFILE is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    PROFILE.append((kind, e0, e1))
+
+
+def launch_count() -> int:
+    L = _lib.lib()
+    L.vrwkv_launch_count.restype = ctypes.c_ulonglong
+    return int(L.vrwkv_launch_count())
+
+
+class WindBackstepping(torch.autograd.Function):
+    """model.py:45-65 — same ops, same allocations, same saved tensors."""
+
+    @staticmethod
+    def forward(ctx, w, q, k, v, z, b):
+        _lib.load_torch_ops()
+        B, T, H, C = w.shape
+        assert T % CHUNK_LEN == 0
+        assert all(i.dtype == torch.bfloat16 for i in [w, q, k, v, z, b])
+        assert all(i.is_contiguous() for i in [w, q, k, v, z, b])
+        y = torch.empty_like(v)
+        s = torch.empty(B, H, T // CHUNK_LEN, C, C, dtype=torch.float32, device=w.device)
+        sa = torch.empty(B, T, H, C, dtype=torch.float32, device=w.device)
+        _timed("fwd", lambda: torch.ops.wind_backstepping.forward(w, q, k, v, z, b, y, s, sa))
+        ctx.save_for_backward(w, q, k, v, z, b, s, sa)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        assert all(i.dtype == torch.bfloat16 for i in [dy])
+        dy = dy.contiguous()  # the reference asserts; autograd may hand us a strided view
+        w, q, k, v, z, b, s, sa = ctx.saved_tensors
+        dw, dq, dk, dv, dz, db = [torch.empty_like(x) for x in [w, q, k, v, z, b]]
+        _timed("bwd", lambda: torch.ops.wind_backstepping.backward(w, q, k, v, z, b, dy, s, sa, dw, dq, dk, dv, dz, db))
+        return dw, dq, dk, dv, dz, db
+
+
+def RUN_CUDA_RWKV7g(q, w, k, v, a, b):
+    """model.py:67-70: six [B,T,H*64] bf16 -> [B,T,H*64] bf16, differentiable in all six."""
+    B, T, HC = q.shape
+    q, w, k, v, a, b = [i.view(B, T, HC // 64, 64) for i in [q, w, k, v, a, b]]
+    return WindBackstepping.apply(w, q, k, v, a, b).view(B, T, HC)
+
+
+def wkv7_forward_state(w, q, k, v, a, b, state_in=None, want_checkpoints: bool = False):
+    """Stateful forward: returns (y, state_out[, s, sa]); inference only (no grad).
+
+    state_in / state_out: f32 [B,H,64,64] (S_ij row-major).  T need not be a multiple of 16 unless
+    checkpoints are requested.
+    """
+    L = _lib.lib()
+    B, T, H, C = w.shape
+    assert C == 64 and all(i.dtype == torch.bfloat16 and i.is_contiguous() and i.is_cuda for i in [w, q, k, v, a, b])
+    y = torch.empty_like(v)
+    state_out = torch.empty(B, H, C, C, dtype=torch.float32, device=w.device)
+    s = sa = None
+    if want_checkpoints:
+        s = torch.empty(B, H, T // CHUNK_LEN, C, C, dtype=torch.float32, device=w.device)
+        sa = torch.empty(B, T, H, C, dtype=torch.float32, device=w.device)
+    if state_in is not None:
+        assert state_in.dtype == torch.float32 and state_in.is_contiguous() and state_in.shape == (B, H, C, C)
+    with torch.cuda.device(w.device):
+        rc = L.vrwkv_wkv7_forward_state(B, T, H, _lib.ptr(w), _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(a),
+                                        _lib.ptr(b), _lib.ptr(y), _lib.ptr(s), _lib.ptr(sa), _lib.ptr(state_in),
+                                        _lib.ptr(state_out), _lib.cur_stream())
+    _lib.check(rc, "vrwkv_wkv7_forward_state")
+    return (y, state_out, s, sa) if want_checkpoints else (y, state_out)
+
+
+def set_variant(fwd: int = 0, bwd: int = 0) -> None:
+    _lib.check(_lib.lib().vrwkv_wkv7_set_variant(ctypes.c_int(fwd), ctypes.c_int(bwd)), "set_variant")
