@@ -137,11 +137,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from oracle import model_ref as MR  # synthetic batch generator only (test infrastructure, not timed math)
     from visualrwkv_b200 import _lib, wkv7
     from visualrwkv_b200.benchutil import ClockSampler
     from visualrwkv_b200.ddp import GradBucketReducer
     from visualrwkv_b200.model import VisualRWKV, default_args, randomize_zero_init
+    from visualrwkv_b200.synthetic import make_batch
     _lib.load_torch_ops()
 
     torch.manual_seed(1234)
@@ -159,7 +159,7 @@ def main():
     opt = torch.optim.AdamW(master, lr=1e-5, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.0, fused=True)
 
     B, T = a.batch, a.ctx
-    host = MR.make_batch(B, T, 576, 224, seed=100 + rank, img_dtype=torch.bfloat16)
+    host = make_batch(B, T, 576, 224, seed=100 + rank, img_dtype=torch.bfloat16)
     host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
     resident = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
@@ -174,9 +174,10 @@ def main():
         loss.backward()
         if reducer is not None:
             reducer.finish()
-        torch._foreach_copy_([m.grad for m in master], [p.grad for p in trainable])
-        opt.step()
-        torch._foreach_copy_(trainable, master)
+        with torch.no_grad():
+            torch._foreach_copy_([m.grad for m in master], [p.grad for p in trainable])
+            opt.step()
+            torch._foreach_copy_(trainable, master)
         return loss
 
     def e2e_step():

@@ -1,0 +1,145 @@
+"""GPU parity of the fused block path (LayerNorm+token-shift mixes, tmix_mid, WKV7, tmix_post, relu^2 and the
+hand-written backward orchestration) against the functional restatement of the reference modules
+(oracle/model_ref.py) evaluated (a) with stock bf16 PyTorch ops on the GPU — the reference's own arithmetic —
+and (b) in fp64 on the CPU with the C oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_ref as MR
+from oracle import wkv7 as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(n_embd, n_layer, seed=0):
+    from visualrwkv_b200.model import RWKV, default_args, randomize_zero_init
+    torch.manual_seed(seed)
+    args = default_args(n_embd=n_embd, n_layer=n_layer, dim_att=n_embd, vocab_size=512)
+    m = RWKV(args)
+    randomize_zero_init(m)
+    # make every parameter "live" so that each gradient is exercised
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if n.endswith(("ln0.weight", "ln1.weight", "ln2.weight", "ln_x.weight", "ln_out.weight")):
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+            if n.endswith(("ln0.bias", "ln1.bias", "ln2.bias", "ln_x.bias", "ln_out.bias", ".a0")):
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+    return m.to(device="cuda", dtype=torch.bfloat16), args
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu().numpy(), b.detach().double().cpu().numpy()
+    return float(np.sqrt(np.mean((a - b) ** 2)) / max(np.sqrt(np.mean(b ** 2)), 1e-30))
+
+
+def _ours_wkv(r, w, k, v, a, b):
+    from visualrwkv_b200.wkv7 import RUN_CUDA_RWKV7g
+    return RUN_CUDA_RWKV7g(*[t.contiguous() for t in (r, w, k, v, a, b)])
+
+
+@pytest.mark.parametrize("n_embd,B,T", [(128, 2, 64), (768, 1, 48)])
+def test_blocks_vs_bf16_eager_reference(n_embd, B, T):
+    m, args = _mk(n_embd, 2)
+    H = n_embd // 64
+    P = {"rwkv." + k: v.detach() for k, v in m.state_dict().items()}
+    torch.manual_seed(5)
+    x0 = (0.5 * torch.randn(B, T, n_embd, device="cuda")).to(torch.bfloat16)
+    gx = torch.randn(B, T, n_embd, device="cuda").to(torch.bfloat16)
+
+    # ours: two blocks chained (layer 0 produces v_first, layer 1 consumes it)
+    xo = x0.clone().requires_grad_(True)
+    x1, vf = m.blocks[0](xo, torch.empty_like(xo))
+    x2, _ = m.blocks[1](x1, vf)
+    (x2.float() * gx.float()).sum().backward()
+
+    # reference arithmetic: stock bf16 torch ops + autograd (WKV7 through our already-verified op)
+    Pr = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    xr = x0.clone().requires_grad_(True)
+    r1, rvf = MR.block(Pr, 0, xr, torch.empty_like(xr), H, _ours_wkv)
+    r2, _ = MR.block(Pr, 1, r1, rvf, H, _ours_wkv)
+    (r2.float() * gx.float()).sum().backward()
+
+    assert _rel(x1, r1) < 1e-2 and _rel(x2, r2) < 1.2e-2  # ~1 bf16 ulp: fused residual add rounds once, eager twice
+    assert _rel(vf, rvf) < 1e-2
+    assert _rel(xo.grad, xr.grad) < 3e-2
+    worst = {}
+    for n, p in m.named_parameters():
+        if p.grad is None:
+            continue
+        ref = Pr["rwkv." + n].grad
+        if ref is None:
+            continue
+        worst[n] = _rel(p.grad, ref)
+    bad = {k: v for k, v in worst.items() if v > 5e-2}
+    assert not bad, bad
+    assert len(worst) > 60
+
+
+def test_block_vs_fp64_oracle():
+    n_embd, B, T = 128, 2, 32
+    m, args = _mk(n_embd, 2, seed=3)
+    H = n_embd // 64
+    torch.manual_seed(7)
+    x0 = (0.5 * torch.randn(B, T, n_embd)).to(torch.bfloat16)
+    gx = torch.randn(B, T, n_embd).to(torch.bfloat16)
+    xo = x0.cuda().requires_grad_(True)
+    x1, vf = m.blocks[0](xo, torch.empty_like(xo))
+    x2, _ = m.blocks[1](x1, vf)
+    (x2.float() * gx.cuda().float()).sum().backward()
+
+    P = {"rwkv." + k: v.detach().double().cpu().requires_grad_(True) for k, v in m.state_dict().items()}
+    xr = x0.double().requires_grad_(True)
+    r1, rvf = MR.block(P, 0, xr, torch.empty_like(xr), H, MR.oracle_wkv("f64"))
+    r2, _ = MR.block(P, 1, r1, rvf, H, MR.oracle_wkv("f64"))
+    (r2 * gx.double()).sum().backward()
+    # bf16 arithmetic vs exact: a few bf16 ulps accumulated over ~40 rounded ops per layer
+    assert _rel(x2.detach().cpu(), r2.detach()) < 2e-2
+    assert _rel(xo.grad.cpu(), xr.grad) < 5e-2
+    for n, p in m.named_parameters():
+        if p.grad is not None and P["rwkv." + n].grad is not None and n.endswith(("weight", "w2", "a2", "g2")) and p.dim() == 2:
+            assert _rel(p.grad.cpu(), P["rwkv." + n].grad) < 8e-2, n
+
+
+def test_standalone_module_api():
+    """RWKV_Tmix_x070 / RWKV_CMix_x070 called the way the reference Block calls them (on ln'ed input)."""
+    m, args = _mk(128, 2, seed=9)
+    H = 2
+    P = {"rwkv." + k: v.detach() for k, v in m.state_dict().items()}
+    torch.manual_seed(1)
+    x = (0.5 * torch.randn(2, 32, 128, device="cuda")).to(torch.bfloat16)
+    a0, vf = m.blocks[0].att(x, torch.empty_like(x))
+    r0, rvf = MR.tmix(P, "rwkv.blocks.0.att.", x, torch.empty_like(x), 0, H, _ours_wkv)
+    assert _rel(a0, r0) < 1e-2 and _rel(vf, rvf) < 1e-2
+    a1, _ = m.blocks[1].att(x, vf)
+    r1, _ = MR.tmix(P, "rwkv.blocks.1.att.", x, rvf, 1, H, _ours_wkv)
+    assert _rel(a1, r1) < 1e-2
+    c = m.blocks[1].ffn(x)
+    rc = MR.cmix(P, "rwkv.blocks.1.ffn.", x)
+    assert _rel(c, rc) < 1e-2
+
+
+def test_layernorm_fn():
+    from visualrwkv_b200 import fused
+    torch.manual_seed(0)
+    for C in (128, 768, 1024):
+        x = torch.randn(3, 40, C, device="cuda").to(torch.bfloat16).requires_grad_(True)
+        w = (1 + 0.1 * torch.randn(C, device="cuda")).to(torch.bfloat16).requires_grad_(True)
+        b = (0.1 * torch.randn(C, device="cuda")).to(torch.bfloat16).requires_grad_(True)
+        g = torch.randn(3, 40, C, device="cuda").to(torch.bfloat16)
+        y = fused.LayerNormFn.apply(x, w, b, 1e-5)
+        y.backward(g)
+        x2, w2, b2 = [t.detach().double().requires_grad_(True) for t in (x, w, b)]
+        y2 = torch.nn.functional.layer_norm(x2, (C,), w2, b2, 1e-5)
+        y2.backward(g.double())
+        assert _rel(y.detach(), y2.detach()) < 3e-3
+        assert _rel(x.grad, x2.grad) < 6e-3 and _rel(w.grad, w2.grad) < 6e-3 and _rel(b.grad, b2.grad) < 6e-3
+
+
+def test_no_cpu_fallback():
+    from visualrwkv_b200.model import RWKV, default_args
+    args = default_args(n_embd=128, n_layer=1, dim_att=128, vocab_size=64)
+    m = RWKV(args)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 16, 128))

@@ -45,7 +45,9 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         for cu, p in procs:
             if p.wait() != 0:
                 raise RuntimeError(f"nvcc failed on {cu}")
-        subprocess.check_call(["nvcc", "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+        # shared cudart: the library must share torch's CUDA runtime instance (same per-thread device/context
+        # state, e.g. on autograd worker threads); torch loads libcudart.so.12 before we are dlopen'ed
+        subprocess.check_call(["nvcc", "-shared", "-cudart", "shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
     return LIB
 
 

@@ -26,6 +26,7 @@ def lib() -> ctypes.CDLL:
             raise NativeLibraryMissing(
                 f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(there is no CPU / PyTorch fallback for the hot path)")
+        import torch  # noqa: F401  (loads the CUDA runtime libvrwkv_b200.so links against)
         _lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
         _lib.vrwkv_last_error.restype = ctypes.c_char_p
     return _lib

@@ -42,6 +42,14 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 int vrwkv_encode_2d(CUtensorMap* m, const void* base, CUtensorMapDataType dt, int elem_bytes, uint64_t cols,
                     uint64_t rows, uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows,
                     CUtensorMapSwizzle swizzle) {
+    // the driver call needs a current context on THIS thread (autograd worker threads may not have touched the
+    // runtime yet): a no-op runtime call binds the primary context of the current device
+    static thread_local bool ctx_ready = false;
+    if (!ctx_ready) {
+        cudaError_t e = cudaFree(nullptr);
+        if (e != cudaSuccess) return vrwkv_fail(VRWKV_ECUDA, "CUDA context init failed: %s", cudaGetErrorString(e));
+        ctx_ready = true;
+    }
     auto enc = get_encode();
     if (!enc) return vrwkv_fail(VRWKV_ECUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     cuuint64_t gdim[2] = {cols, rows};

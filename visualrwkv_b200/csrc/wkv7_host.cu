@@ -11,6 +11,8 @@
 #include "host_util.h"
 #include "wkv7_bwd.cuh"
 #include "wkv7_fwd.cuh"
+#include "wkv7_bwd2.cuh"
+#include "wkv7_fwd2.cuh"
 
 using namespace vrwkv;
 
@@ -61,6 +63,30 @@ static int launch_bwd(const CUtensorMap* tm, const Wkv7BwdArgs& a, cudaStream_t 
     return VRWKV_OK;
 }
 
+template <int R, int NSTAGE>
+static int launch_fwd2(const CUtensorMap* tm, const Wkv7FwdArgs& a, cudaStream_t st) {
+    auto kern = wkv7_fwd2_kernel<R, NSTAGE>;
+    const size_t smem = sizeof(Wkv7Fwd2Smem<NSTAGE>) + 128;
+    VRWKV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(a.H, a.B), block((WKV_N / R) * 8 + 32);
+    kern<<<grid, block, smem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], a);
+    VRWKV_CUDA(cudaGetLastError());
+    vrwkv_count_launch(1);
+    return VRWKV_OK;
+}
+
+template <int R, int NSTAGE>
+static int launch_bwd2(const CUtensorMap* tm, const Wkv7BwdArgs& a, cudaStream_t st) {
+    auto kern = wkv7_bwd2_kernel<R, NSTAGE>;
+    const size_t smem = sizeof(Wkv7Bwd2Smem<NSTAGE>) + 128;
+    VRWKV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(a.H, a.B), block((WKV_N / R) * 8 + 32);
+    kern<<<grid, block, smem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], tm[7], a);
+    VRWKV_CUDA(cudaGetLastError());
+    vrwkv_count_launch(1);
+    return VRWKV_OK;
+}
+
 static int check_common(int B, int T, int H, const void* const* ptrs, int nptr) {
     if (B <= 0 || T <= 0 || H <= 0) return vrwkv_fail(VRWKV_EINVAL, "wkv7: B,T,H must be positive (got %d,%d,%d)", B, T, H);
     if ((long long)B * T >= (1ll << 31)) return vrwkv_fail(VRWKV_EUNSUP, "wkv7: B*T too large");
@@ -88,13 +114,15 @@ extern "C" int vrwkv_wkv7_forward_state(int B, int T, int H, const uint16_t* w, 
     Wkv7FwdArgs args{B, T, H, y, s, sa, state_in, state_out};
     cudaStream_t st = (cudaStream_t)stream;
     int var = g_fwd_variant.load();
-    if (var == 0) var = 5;
+    if (var == 0) var = 6;
     switch (var) {
         case 1: return launch_fwd<4, 2, 4, 4>(tm, args, st);
         case 2: return launch_fwd<2, 1, 4, 4>(tm, args, st);
         case 3: return launch_fwd<4, 1, 4, 4>(tm, args, st);
         case 4: return launch_fwd<8, 1, 4, 4>(tm, args, st);
         case 5: return launch_fwd<8, 2, 4, 4>(tm, args, st);
+        case 6: return launch_fwd2<4, 4>(tm, args, st);
+        case 7: return launch_fwd2<2, 4>(tm, args, st);
         default: return vrwkv_fail(VRWKV_EINVAL, "wkv7 forward: unknown variant %d", var);
     }
 }
@@ -123,11 +151,13 @@ extern "C" int vrwkv_wkv7_backward(int B, int T, int H, const uint16_t* w, const
     Wkv7BwdArgs args{B, T, H, s, dw, dq, dk, dv, da, db};
     cudaStream_t st = (cudaStream_t)stream;
     int var = g_bwd_variant.load();
-    if (var == 0) var = 2;
+    if (var == 0) var = 4;
     switch (var) {
         case 1: return launch_bwd<4, 4, 3>(tm, args, st);
         case 2: return launch_bwd<2, 4, 3>(tm, args, st);
         case 3: return launch_bwd<8, 4, 3>(tm, args, st);
+        case 4: return launch_bwd2<4, 3>(tm, args, st);
+        case 5: return launch_bwd2<2, 3>(tm, args, st);
         default: return vrwkv_fail(VRWKV_EINVAL, "wkv7 backward: unknown variant %d", var);
     }
 }

@@ -1,0 +1,330 @@
+"""Python front-end of the fused row-wise kernels (csrc/fused_ln.cu, csrc/fused_tmix.cu) and the two
+hand-written autograd nodes that orchestrate one RWKV-7 block:
+
+  TmixBlockFn :  x -> x + att(ln1(x))      (VisualRWKV-v7/v7.00/src/model.py:250-251 with :163-195 inside)
+  CmixBlockFn :  x -> x + ffn(ln2(x))      (model.py:252 with :221-227 inside)
+
+GEMMs are plain library GEMMs (cuBLAS through torch.matmul / addmm); everything else on the path is one of
+our sm_100a kernels reached through the C ABI.  The backward passes are written out by hand (no autograd
+tracing inside the block): they call the backward kernels, accumulate residual gradients in the LayerNorm
+backward and reduce per-channel parameter gradients from per-CTA fp32 partials.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from . import wkv7 as _wkv7
+
+_c_int, _c_float, _c_void_p, _c_size_t = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+
+
+def _p(t):
+    return _c_void_p(0 if t is None else t.data_ptr())
+
+
+def _parr(ts):
+    return (_c_void_p * max(len(ts), 1))(*[t.data_ptr() for t in ts])
+
+
+def _chk(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed ({rc}): {_lib.lib().vrwkv_last_error().decode()}")
+
+
+def _bf16c(*ts):
+    for t in ts:
+        assert t is None or (t.dtype == torch.bfloat16 and t.is_contiguous() and t.is_cuda), "expected contiguous CUDA bf16"
+
+
+# ------------------------------------------------------------------------------------------------------
+# thin kernel wrappers
+# ------------------------------------------------------------------------------------------------------
+def ln_mix_forward(x2d, T, gamma, beta, eps, coefs, want_h=False):
+    """x2d [rows,C] bf16 -> (list of mixed streams, h or None, stats[rows,2] f32)."""
+    L = _lib.lib()
+    rows, C = x2d.shape
+    _bf16c(x2d, gamma, beta, *coefs)
+    outs = [torch.empty_like(x2d) for _ in coefs]
+    h = torch.empty_like(x2d) if (want_h or not coefs) else None
+    stats = torch.empty(rows, 2, dtype=torch.float32, device=x2d.device)
+    rc = L.vrwkv_ln_mix_forward(_c_int(rows), _c_int(T), _c_int(C), _c_int(len(coefs)), _c_float(eps), _p(x2d), _p(gamma),
+                                _p(beta), _parr(coefs), _parr(outs), _p(h), _p(stats), _lib.cur_stream())
+    _chk(rc, "vrwkv_ln_mix_forward")
+    return outs, h, stats
+
+
+def ln_mix_backward(x2d, T, stats, gamma, beta, coefs, douts, dh=None, dresid=None):
+    """-> (dx, dgamma, dbeta, [dcoef...]) ; gradients of parameters in fp32."""
+    L = _lib.lib()
+    rows, C = x2d.shape
+    _bf16c(x2d, gamma, beta, dh, dresid, *coefs, *douts)
+    nb = L.vrwkv_ln_mix_blocks(_c_int(rows))
+    partial = torch.empty(nb, 2 + len(coefs), C, dtype=torch.float32, device=x2d.device)
+    dx = torch.empty_like(x2d)
+    rc = L.vrwkv_ln_mix_backward(_c_int(rows), _c_int(T), _c_int(C), _c_int(len(coefs)), _p(x2d), _p(stats), _p(gamma), _p(beta),
+                                 _parr(coefs), _parr(douts), _p(dh), _p(dresid), _p(dx), _p(partial), _lib.cur_stream())
+    _chk(rc, "vrwkv_ln_mix_backward")
+    red = partial.sum(0)
+    return dx, red[0], red[1], [red[2 + i] for i in range(len(coefs))]
+
+
+def tmix_mid_forward(k, v, vfirst, ww, aa, vv, w0, a0, v0, k_k, k_a):
+    L = _lib.lib()
+    rows, C = k.shape
+    _bf16c(k, v, vfirst, ww, aa, vv, w0, a0, v0, k_k, k_a)
+    outs = [torch.empty_like(k) for _ in range(5)]
+    rc = L.vrwkv_tmix_mid_forward(_c_int(rows), _c_int(C), _p(k), _p(v), _p(vfirst), _p(ww), _p(aa), _p(vv), _p(w0), _p(a0),
+                                  _p(v0), _p(k_k), _p(k_a), *[_p(o) for o in outs], _lib.cur_stream())
+    _chk(rc, "vrwkv_tmix_mid_forward")
+    return outs  # w, k2, v2, nkk, kka
+
+
+def tmix_mid_backward(k, v, vfirst, ww, aa, vv, w0, a0, v0, k_k, k_a, dw, dk2, dv2, dnkk, dkka):
+    L = _lib.lib()
+    rows, C = k.shape
+    _bf16c(k, v, vfirst, ww, aa, vv, dw, dk2, dv2, dnkk, dkka)
+    has = vfirst is not None
+    dk, dv, dww, daa = [torch.empty_like(k) for _ in range(4)]
+    dvf = torch.empty_like(k) if has else None
+    dvv = torch.empty_like(k) if has else None
+    nb = L.vrwkv_tmix_blocks(_c_int(rows))
+    partial = torch.empty(nb, 5, C, dtype=torch.float32, device=k.device)
+    rc = L.vrwkv_tmix_mid_backward(_c_int(rows), _c_int(C), _p(k), _p(v), _p(vfirst), _p(ww), _p(aa), _p(vv), _p(w0), _p(a0),
+                                   _p(v0), _p(k_k), _p(k_a), _p(dw), _p(dk2), _p(dv2), _p(dnkk), _p(dkka), _p(dk), _p(dv),
+                                   _p(dvf), _p(dww), _p(daa), _p(dvv), _p(partial), _lib.cur_stream())
+    _chk(rc, "vrwkv_tmix_mid_backward")
+    red = partial.sum(0)
+    return dk, dv, dvf, dww, daa, dvv, red  # red rows: dw0, da0, dv0, dk_k, dk_a
+
+
+def tmix_post_forward(y, r, k2, v2, g, gamma, beta, r_k, eps):
+    L = _lib.lib()
+    rows, C = y.shape
+    _bf16c(y, r, k2, v2, g, gamma, beta, r_k)
+    z = torch.empty_like(y)
+    rc = L.vrwkv_tmix_post_forward(_c_int(rows), _c_int(C), _c_float(eps), _p(y), _p(r), _p(k2), _p(v2), _p(g), _p(gamma),
+                                   _p(beta), _p(r_k), _p(z), _lib.cur_stream())
+    _chk(rc, "vrwkv_tmix_post_forward")
+    return z
+
+
+def tmix_post_backward(y, r, k2, v2, g, gamma, beta, r_k, eps, dz):
+    L = _lib.lib()
+    rows, C = y.shape
+    _bf16c(y, r, k2, v2, g, dz)
+    dy, dr, dk2, dv2, dg = [torch.empty_like(y) for _ in range(5)]
+    nb = L.vrwkv_tmix_blocks(_c_int(rows))
+    partial = torch.empty(nb, 3, C, dtype=torch.float32, device=y.device)
+    rc = L.vrwkv_tmix_post_backward(_c_int(rows), _c_int(C), _c_float(eps), _p(y), _p(r), _p(k2), _p(v2), _p(g), _p(gamma),
+                                    _p(beta), _p(r_k), _p(dz), _p(dy), _p(dr), _p(dk2), _p(dv2), _p(dg), _p(partial),
+                                    _lib.cur_stream())
+    _chk(rc, "vrwkv_tmix_post_backward")
+    red = partial.sum(0)
+    return dy, dr, dk2, dv2, dg, red  # red rows: dgamma, dbeta, dr_k
+
+
+def relu_sq_forward(x):
+    L = _lib.lib()
+    _bf16c(x)
+    y = torch.empty_like(x)
+    _chk(L.vrwkv_relu_sq_forward(_c_size_t(x.numel()), _p(x), _p(y), _lib.cur_stream()), "vrwkv_relu_sq_forward")
+    return y
+
+
+def relu_sq_backward(x, dy):
+    L = _lib.lib()
+    _bf16c(x, dy)
+    dx = torch.empty_like(x)
+    _chk(L.vrwkv_relu_sq_backward(_c_size_t(x.numel()), _p(x), _p(dy), _p(dx), _lib.cur_stream()), "vrwkv_relu_sq_backward")
+    return dx
+
+
+def wkv7_fwd_raw(w, q, k, v, a, b):
+    """[B,T,H,64] bf16 x6 -> y, s, sa through torch.ops.wind_backstepping (timed when wkv7.PROFILE is set)."""
+    _lib.load_torch_ops()
+    B, T, H, C = w.shape
+    y = torch.empty_like(v)
+    s = torch.empty(B, H, T // 16, C, C, dtype=torch.float32, device=w.device)
+    sa = torch.empty(B, T, H, C, dtype=torch.float32, device=w.device)
+    _wkv7._timed("fwd", lambda: torch.ops.wind_backstepping.forward(w, q, k, v, a, b, y, s, sa))
+    return y, s, sa
+
+
+def wkv7_bwd_raw(w, q, k, v, a, b, dy, s, sa):
+    outs = [torch.empty_like(w) for _ in range(6)]
+    _wkv7._timed("bwd", lambda: torch.ops.wind_backstepping.backward(w, q, k, v, a, b, dy, s, sa, *outs))
+    return outs  # dw, dq, dk, dv, da, db
+
+
+# ------------------------------------------------------------------------------------------------------
+# plain LayerNorm node (ln0, ln_out, proj.ln_v)
+# ------------------------------------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1]).contiguous()
+        _, h, stats = ln_mix_forward(x2, x2.shape[0], weight, bias, eps, [], want_h=True)
+        ctx.save_for_backward(x2, stats, weight, bias)
+        ctx.shp = shp
+        return h.view(shp)
+
+    @staticmethod
+    def backward(ctx, dh):
+        x2, stats, weight, bias = ctx.saved_tensors
+        dh2 = dh.reshape(x2.shape).contiguous()
+        dx, dg, db, _ = ln_mix_backward(x2, x2.shape[0], stats, weight, bias, [], [], dh=dh2)
+        return dx.view(ctx.shp), dg.to(weight.dtype), db.to(bias.dtype), None
+
+
+# ------------------------------------------------------------------------------------------------------
+# time-mix half block
+# ------------------------------------------------------------------------------------------------------
+_TM_PARAMS = ["x_r", "x_w", "x_k", "x_v", "x_a", "x_g", "w0", "w1", "w2", "a0", "a1", "a2", "v0", "v1", "v2", "g1", "g2",
+              "k_k", "k_a", "r_k"]
+
+
+class TmixBlockFn(torch.autograd.Function):
+    """(x, v_first, ln1.w, ln1.b, <20 att params>, Wr, Wk, Wv, Wo, lnx.w, lnx.b) -> (x + att(ln1(x)), v_first)."""
+
+    @staticmethod
+    def forward(ctx, x, v_first, ln_w, ln_b, x_r, x_w, x_k, x_v, x_a, x_g, w0, w1, w2, a0, a1, a2, v0, v1, v2, g1, g2, k_k, k_a,
+                r_k, Wr, Wk, Wv, Wo, lnx_w, lnx_b, layer_id, n_head, ln_eps, gn_eps, with_ln):
+        B, T, C = x.shape
+        rows = B * T
+        x2 = x.reshape(rows, C).contiguous()
+        coefs = [c.reshape(C) for c in (x_r, x_w, x_k, x_v, x_a, x_g)]
+        (xr, xw, xk, xv, xa, xg), _, stats = ln_mix_forward(x2, T, ln_w if with_ln else None, ln_b if with_ln else None, ln_eps, coefs)
+        r = xr @ Wr.t()
+        k = xk @ Wk.t()
+        v = xv @ Wv.t()
+        hw = torch.tanh(xw @ w1)
+        ww = hw @ w2
+        ha = xa @ a1
+        aa = ha @ a2
+        hg = torch.sigmoid(xg @ g1)
+        g = hg @ g2
+        has_vres = layer_id != 0
+        if has_vres:
+            hv = xv @ v1
+            vv = hv @ v2
+            vf2 = v_first.reshape(rows, C).contiguous()
+        else:
+            hv = vv = vf2 = None
+        w, k2, v2_, nkk, kka = tmix_mid_forward(k, v, vf2, ww, aa, vv, w0.reshape(C), a0.reshape(C),
+                                                v0.reshape(C) if has_vres else None, k_k.reshape(C), k_a.reshape(C))
+        H = n_head
+        v4 = lambda t: t.view(B, T, H, 64)
+        y, s, sa = wkv7_fwd_raw(v4(w), v4(r), v4(k2), v4(v2_), v4(nkk), v4(kka))
+        z = tmix_post_forward(y.view(rows, C), r, k2, v2_, g, lnx_w, lnx_b, r_k.reshape(C), gn_eps)
+        out = torch.addmm(x2, z, Wo.t()) if with_ln else z @ Wo.t()
+        ctx.save_for_backward(x2, stats, ln_w, ln_b, *coefs, xr, xw, xk, xv, xa, xg, r, k, v, hw, ww, ha, aa, hg, g, hv, vv, vf2,
+                              w, k2, v2_, nkk, kka, y, s, sa, z, w0, w1, w2, a0, a1, a2, v0, v1, v2, g1, g2, k_k, k_a, r_k,
+                              Wr, Wk, Wv, Wo, lnx_w, lnx_b)
+        ctx.meta = (B, T, C, H, layer_id, ln_eps, gn_eps, with_ln)
+        v_out = v.view(B, T, C)  # layer 0: this is v_first; later layers: ignored by the caller
+        if has_vres:
+            ctx.mark_non_differentiable(v_out)
+        return out.view(B, T, C), v_out
+
+    @staticmethod
+    def backward(ctx, dout, dvfirst_out):
+        (x2, stats, ln_w, ln_b, c_r, c_w, c_k, c_v, c_a, c_g, xr, xw, xk, xv, xa, xg, r, k, v, hw, ww, ha, aa, hg, g, hv, vv, vf2,
+         w, k2, v2_, nkk, kka, y, s, sa, z, w0, w1, w2, a0, a1, a2, v0, v1, v2, g1, g2, k_k, k_a, r_k, Wr, Wk, Wv, Wo, lnx_w,
+         lnx_b) = ctx.saved_tensors
+        B, T, C, H, layer_id, ln_eps, gn_eps, with_ln = ctx.meta
+        rows = B * T
+        has_vres = layer_id != 0
+        do = dout.reshape(rows, C).contiguous()
+        dz = do @ Wo
+        dWo = do.t() @ z
+        dy, dr, dk2a, dv2a, dg, red3 = tmix_post_backward(y.view(rows, C), r, k2, v2_, g, lnx_w, lnx_b, r_k.reshape(C), gn_eps, dz)
+        v4 = lambda t: t.view(B, T, H, 64)
+        dw, dq, dk2b, dv2b, dnkk, dkka = wkv7_bwd_raw(v4(w), v4(r), v4(k2), v4(v2_), v4(nkk), v4(kka), v4(dy), s, sa)
+        dr.add_(dq.view(rows, C))
+        dk2a.add_(dk2b.view(rows, C))
+        dv2a.add_(dv2b.view(rows, C))
+        dk, dv, dvf, dww, daa, dvv, red5 = tmix_mid_backward(
+            k, v, vf2, ww, aa, vv, w0.reshape(C), a0.reshape(C), v0.reshape(C) if has_vres else None, k_k.reshape(C),
+            k_a.reshape(C), dw.view(rows, C), dk2a, dv2a, dnkk.view(rows, C), dkka.view(rows, C))
+        if not has_vres and dvfirst_out is not None:
+            dv.add_(dvfirst_out.reshape(rows, C))
+        # LoRA branches
+        dhg = dg @ g2.t()
+        dg2 = hg.t() @ dg
+        dpg = dhg * (hg * (1 - hg))
+        dxg = dpg @ g1.t()
+        dg1 = xg.t() @ dpg
+        dhw = dww @ w2.t()
+        dw2 = hw.t() @ dww
+        dpw = dhw * (1 - hw * hw)
+        dxw = dpw @ w1.t()
+        dw1 = xw.t() @ dpw
+        dha = daa @ a2.t()
+        da2 = ha.t() @ daa
+        dxa = dha @ a1.t()
+        da1 = xa.t() @ dha
+        # main projections
+        dxr = dr @ Wr
+        dWr = dr.t() @ xr
+        dxk = dk @ Wk
+        dWk = dk.t() @ xk
+        dWv = dv.t() @ xv
+        if has_vres:
+            dhv = dvv @ v2.t()
+            dv2p = hv.t() @ dvv
+            dv1 = xv.t() @ dhv
+            dxv = torch.addmm(dhv @ v1.t(), dv, Wv)
+        else:
+            dxv = dv @ Wv
+            dv2p = dv1 = None
+        coefs = [c_r, c_w, c_k, c_v, c_a, c_g]
+        dx, dlnw, dlnb, dco = ln_mix_backward(x2, T, stats, ln_w if with_ln else None, ln_b if with_ln else None, coefs,
+                                              [dxr, dxw, dxk, dxv, dxa, dxg], dresid=do if with_ln else None)
+        pd = w0.dtype
+        sh = lambda t: t.to(pd).view(1, 1, C)
+        grads = [dx.view(B, T, C), dvf.view(B, T, C) if has_vres else None,
+                 dlnw.to(pd) if with_ln else None, dlnb.to(pd) if with_ln else None,
+                 sh(dco[0]), sh(dco[1]), sh(dco[2]), sh(dco[3]), sh(dco[4]), sh(dco[5]),
+                 sh(red5[0]), dw1, dw2, sh(red5[1]), da1, da2,
+                 sh(red5[2]) if has_vres else None, dv1, dv2p, dg1, dg2, sh(red5[3]), sh(red5[4]),
+                 red3[2].to(pd).view(H, 64), dWr, dWk, dWv, dWo, red3[0].to(pd), red3[1].to(pd),
+                 None, None, None, None, None]
+        return tuple(grads)
+
+
+class CmixBlockFn(torch.autograd.Function):
+    """(x, ln2.w, ln2.b, x_k, Wkey, Wval) -> x + value(relu(key(mix(ln2(x))))^2)."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, x_k, Wkey, Wval, ln_eps, with_ln):
+        B, T, C = x.shape
+        rows = B * T
+        x2 = x.reshape(rows, C).contiguous()
+        ck = x_k.reshape(C)
+        (xk,), _, stats = ln_mix_forward(x2, T, ln_w if with_ln else None, ln_b if with_ln else None, ln_eps, [ck])
+        hk = xk @ Wkey.t()
+        act = relu_sq_forward(hk)
+        out = torch.addmm(x2, act, Wval.t()) if with_ln else act @ Wval.t()
+        ctx.save_for_backward(x2, stats, ln_w, ln_b, ck, xk, hk, act, Wkey, Wval)
+        ctx.meta = (B, T, C, with_ln)
+        return out.view(B, T, C)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, stats, ln_w, ln_b, ck, xk, hk, act, Wkey, Wval = ctx.saved_tensors
+        B, T, C, with_ln = ctx.meta
+        do = dout.reshape(B * T, C).contiguous()
+        dact = do @ Wval
+        dWval = do.t() @ act
+        dhk = relu_sq_backward(hk, dact)
+        dxk = dhk @ Wkey
+        dWkey = dhk.t() @ xk
+        dx, dlnw, dlnb, dco = ln_mix_backward(x2, T, stats, ln_w if with_ln else None, ln_b if with_ln else None, [ck], [dxk],
+                                              dresid=do if with_ln else None)
+        pd = ck.dtype
+        return (dx.view(B, T, C), dlnw.to(pd) if with_ln else None, dlnb.to(pd) if with_ln else None, dco[0].to(pd).view(1, 1, C),
+                dWkey, dWval, None, None)

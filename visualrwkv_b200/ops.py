@@ -1,8 +1,8 @@
 """Operator layer between the reference-shaped modules (model.py) and the native kernels.
 
-Each function cites the reference lines it implements.  GEMMs that are plain library GEMMs go to
-cuBLAS through torch.matmul; everything else on the path is a hand-written sm_100a kernel reached
-through the C ABI (fused.py) — there is no CPU path here.
+Each function cites the reference lines it implements.  Plain GEMMs go to cuBLAS through torch.matmul;
+everything else on the path is a hand-written sm_100a kernel reached through the C ABI (fused.py, wkv7.py).
+There is no CPU / eager fallback here: CUDA bf16 tensors are required and the native library must load.
 """
 from __future__ import annotations
 
@@ -11,68 +11,60 @@ import warnings
 import torch
 import torch.nn.functional as F
 
-from .wkv7 import RUN_CUDA_RWKV7g
+from . import fused
 
 
-def _shift(x):
-    """nn.ZeroPad2d((0,0,1,-1)) (model.py:149)."""
-    return torch.cat([torch.zeros_like(x[:, :1]), x[:, :-1]], dim=1)
+def _need_cuda_bf16(x, what):
+    if not (x.is_cuda and x.dtype == torch.bfloat16):
+        raise RuntimeError(f"{what}: the sm_100a path needs CUDA bf16 tensors (got {x.device}, {x.dtype}); "
+                           "there is no CPU / fp32 fallback")
 
 
 def layer_norm(x, ln):
-    return F.layer_norm(x, (x.shape[-1],), ln.weight, ln.bias, ln.eps)
+    _need_cuda_bf16(x, "layer_norm")
+    return fused.LayerNormFn.apply(x, ln.weight, ln.bias, ln.eps)
+
+
+def _tmix_args(m):
+    has = m.layer_id != 0
+    return (m.x_r, m.x_w, m.x_k, m.x_v, m.x_a, m.x_g, m.w0, m.w1, m.w2, m.a0, m.a1, m.a2,
+            m.v0 if has else None, m.v1 if has else None, m.v2 if has else None, m.g1, m.g2, m.k_k, m.k_a, m.r_k,
+            m.receptance.weight, m.key.weight, m.value.weight, m.output.weight, m.ln_x.weight, m.ln_x.bias)
 
 
 def tmix_forward(m, x, v_first):
-    """RWKV_Tmix_x070.forward (model.py:163-195)."""
-    B, T, C = x.size()
-    H = m.n_head
-    xx = _shift(x) - x
-    xr = x + xx * m.x_r
-    xw = x + xx * m.x_w
-    xk = x + xx * m.x_k
-    xv = x + xx * m.x_v
-    xa = x + xx * m.x_a
-    xg = x + xx * m.x_g
-    r = m.receptance(xr)
-    w = -F.softplus(-(m.w0 + torch.tanh(xw @ m.w1) @ m.w2)) - 0.5
-    k = m.key(xk)
-    v = m.value(xv)
-    if m.layer_id == 0:
-        v_first = v
-    else:
-        v = v + (v_first - v) * torch.sigmoid(m.v0 + (xv @ m.v1) @ m.v2)
-    a = torch.sigmoid(m.a0 + (xa @ m.a1) @ m.a2)
-    g = torch.sigmoid(xg @ m.g1) @ m.g2
-    kk = F.normalize((k * m.k_k).view(B, T, H, -1), dim=-1, p=2.0).view(B, T, C)
-    k = k * (1 + (a - 1) * m.k_a)
-    y = RUN_CUDA_RWKV7g(r.contiguous(), w.contiguous(), k.contiguous(), v.contiguous(), (-kk).contiguous(),
-                        (kk * a).contiguous())
-    y = F.group_norm(y.view(B * T, C), H, m.ln_x.weight, m.ln_x.bias, m.ln_x.eps).view(B, T, C)
-    y = y + ((r.view(B, T, H, -1) * k.view(B, T, H, -1) * m.r_k).sum(dim=-1, keepdim=True) * v.view(B, T, H, -1)).view(B, T, C)
-    return m.output(y * g), v_first
+    """RWKV_Tmix_x070.forward (model.py:163-195) on an already layer-normed x: returns (att_out, v_first)."""
+    _need_cuda_bf16(x, "RWKV_Tmix_x070")
+    out, v = fused.TmixBlockFn.apply(x, v_first if m.layer_id != 0 else None, None, None, *_tmix_args(m),
+                                     m.layer_id, m.n_head, 1e-5, m.ln_x.eps, False)
+    return out, (v if m.layer_id == 0 else v_first)
 
 
 def cmix_forward(m, x):
-    """RWKV_CMix_x070.forward (model.py:221-227)."""
-    xx = _shift(x) - x
-    k = x + xx * m.x_k
-    k = torch.relu(m.key(k)) ** 2
-    return m.value(k)
+    """RWKV_CMix_x070.forward (model.py:221-227) on an already layer-normed x."""
+    _need_cuda_bf16(x, "RWKV_CMix_x070")
+    return fused.CmixBlockFn.apply(x, None, None, m.x_k, m.key.weight, m.value.weight, 1e-5, False)
 
 
 def block_forward(blk, x, v_first):
-    """Block.forward (model.py:247-254)."""
+    """Block.forward (model.py:247-254): [ln0] ; x += att(ln1 x) ; x += ffn(ln2 x), LayerNorms and residual adds
+    fused into the neighbouring kernels."""
+    _need_cuda_bf16(x, "Block")
     if blk.layer_id == 0:
         x = layer_norm(x, blk.ln0)
-    xx, v_first = blk.att(layer_norm(x, blk.ln1), v_first)
-    x = x + xx
-    x = x + blk.ffn(layer_norm(x, blk.ln2))
+    m = blk.att
+    x, v = fused.TmixBlockFn.apply(x, v_first if blk.layer_id != 0 else None, blk.ln1.weight, blk.ln1.bias, *_tmix_args(m),
+                                   blk.layer_id, m.n_head, blk.ln1.eps, m.ln_x.eps, True)
+    if blk.layer_id == 0:
+        v_first = v
+    f = blk.ffn
+    x = fused.CmixBlockFn.apply(x, blk.ln2.weight, blk.ln2.bias, f.x_k, f.key.weight, f.value.weight, blk.ln2.eps, True)
     return x, v_first
 
 
 def projector_forward(m, x):
-    """MLPWithContextGating.forward (model.py:335-338)."""
+    """MLPWithContextGating.forward (model.py:335-338): LN(o_proj(x * sigmoid(gate(x))))."""
+    _need_cuda_bf16(x, "MLPWithContextGating")
     gating = torch.sigmoid(m.gate(x))
     return layer_norm(m.o_proj(x * gating), m.ln_v)
 
@@ -89,8 +81,8 @@ def adaptive_pooling(feats, out_hw):
 
 
 def embed_and_scatter(emb_weight, input_ids, image_features, image_token_index, sample_ids=None):
-    """preparing_embedding (model.py:481-493): emb(input_ids) with the rows where ids == 65535 replaced by
-    the image features in row-major order of appearance (bit-exact copy)."""
+    """preparing_embedding (model.py:481-493): emb(input_ids) with the rows where ids == 65535 replaced by the
+    image features in row-major order of appearance (bit-exact copy; gradient flows to the features)."""
     B, L = input_ids.shape
     D = emb_weight.shape[1]
     x = F.embedding(input_ids, emb_weight).view(B * L, D)
@@ -100,14 +92,8 @@ def embed_and_scatter(emb_weight, input_ids, image_features, image_token_index, 
     if n_sel != feats.shape[0]:
         warnings.warn(f"sample_id: {':::'.join(sample_ids or [])}, image tokens: {n_sel}, but image features: {feats.shape[0]}")
         feats = feats[:n_sel]
-    x = x.clone() if not x.requires_grad and not feats.requires_grad else x
-    x = x.masked_scatter(sel.unsqueeze(-1), feats.to(x.dtype)) if feats.requires_grad or x.requires_grad else _scatter_inplace(x, sel, feats)
+    x = x.masked_scatter(sel.unsqueeze(-1), feats.to(x.dtype))
     return x.view(B, L, D)
-
-
-def _scatter_inplace(x, sel, feats):
-    x[sel] = feats.to(x.dtype)
-    return x
 
 
 def training_loss(logits, targets, ignore_index, l2wrap):
