@@ -199,7 +199,9 @@ def siglip_forward(P, pixels, cfg, pre="vit."):
         q = F.linear(h, P[lp + "self_attn.q_proj.weight"], P[lp + "self_attn.q_proj.bias"]).view(N, S, nh, hd).transpose(1, 2)
         k = F.linear(h, P[lp + "self_attn.k_proj.weight"], P[lp + "self_attn.k_proj.bias"]).view(N, S, nh, hd).transpose(1, 2)
         v = F.linear(h, P[lp + "self_attn.v_proj.weight"], P[lp + "self_attn.v_proj.bias"]).view(N, S, nh, hd).transpose(1, 2)
-        att = torch.softmax((q @ k.transpose(-1, -2)).float() * hd ** -0.5, dim=-1).to(q.dtype)
+        sc = q @ k.transpose(-1, -2)
+        sc = sc.float() if sc.dtype in (torch.bfloat16, torch.float16) else sc  # softmax in >= fp32 (HF eager)
+        att = torch.softmax(sc * hd ** -0.5, dim=-1).to(q.dtype)
         o = (att @ v).transpose(1, 2).reshape(N, S, D)
         x = x + F.linear(o, P[lp + "self_attn.out_proj.weight"], P[lp + "self_attn.out_proj.bias"])
         h = F.layer_norm(x, (D,), P[lp + "layer_norm2.weight"], P[lp + "layer_norm2.bias"], cfg["eps"])

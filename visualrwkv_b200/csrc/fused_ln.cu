@@ -30,7 +30,7 @@ struct LnMixFwdArgs {
     float* stats;     // [rows][2] mean, rstd
 };
 
-__device__ __forceinline__ void ln_row(const F8& x, float inv_c, float eps, float* red, int& phase, int nwarps,
+__device__ __forceinline__ void ln_row(const F8& x, bool active, float inv_c, float eps, float* red, int& phase, int nwarps,
                                        float& mean, float& rstd) {
     float s[1] = {0.f};
 #pragma unroll
@@ -40,7 +40,7 @@ __device__ __forceinline__ void ln_row(const F8& x, float inv_c, float eps, floa
     float q[1] = {0.f};
 #pragma unroll
     for (int e = 0; e < 8; e++) {
-        const float d = x.v[e] - mean;
+        const float d = active ? x.v[e] - mean : 0.f;  // padding threads (c0 >= C) must not add mean^2
         q[0] += d * d;
     }
     block_sum<1>(q, red, phase, nwarps);
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) ln_mix_fwd_kernel(const LnMixFwdArgs a) {
     auto ln_or_id = [&](const F8& x, int row, bool write_stats) {
         if (!do_ln) return x;
         float mean, rstd;
-        ln_row(x, inv_c, a.eps, red, phase, nwarps, mean, rstd);
+        ln_row(x, active, inv_c, a.eps, red, phase, nwarps, mean, rstd);
         if (write_stats && tid == 0 && a.stats) {
             a.stats[2 * row] = mean;
             a.stats[2 * row + 1] = rstd;

@@ -324,8 +324,13 @@ class VisualRWKV(_Base):
 
     def training_step(self, batch, batch_idx=0):
         """model.py:418-434: shifted CE / valid length per sample, batch mean, L2Wrap."""
-        logits, targets = self(batch)
-        return ops.training_loss(logits, targets, IGNORE_INDEX, L2Wrap)
+        x, targets = self.preparing_embedding(batch)
+        feats, pad = self.rwkv.forward_features(x)
+        if pad:  # left-padded rows carry no label (model.py:309-312,325)
+            feats = feats[:, pad:]
+        # head + shifted CE + L2Wrap in two passes over the logits (ops.head_loss); `self(batch)` followed by
+        # ops.training_loss(logits, targets, ...) is the unfused, reference-shaped equivalent
+        return ops.head_loss(feats.contiguous(), self.rwkv.head.weight, targets, IGNORE_INDEX)
 
     @torch.no_grad()
     def generate(self, input_ids, images, do_sample, temperature, top_p, max_new_tokens, stop_token_idx):

@@ -105,3 +105,9 @@ def training_loss(logits, targets, ignore_index, l2wrap):
                            ignore_index=ignore_index, reduction="none")
     loss = (loss.view(shift_labels.size()).sum(1) / valid).mean()
     return l2wrap.apply(loss, logits)
+
+
+def head_loss(features, head_weight, targets, ignore_index):
+    """head GEMM + training_step loss + L2Wrap fused (model.py:323-325, 418-434, 257-271); `features` = ln_out output."""
+    _need_cuda_bf16(features, "head_loss")
+    return fused.HeadLossFn.apply(features, head_weight, targets, ignore_index)
