@@ -30,21 +30,32 @@ struct LnMixFwdArgs {
     float* stats;     // [rows][2] mean, rstd
 };
 
-__device__ __forceinline__ void ln_row(const F8& x, bool active, float inv_c, float eps, float* red, int& phase, int nwarps,
-                                       float& mean, float& rstd) {
-    float s[1] = {0.f};
+// mean / rstd of NB rows at once: two block reductions for NB rows instead of two per row
+template <int NB>
+__device__ __forceinline__ void ln_stats(const F8 (&x)[NB], bool active, float inv_c, float eps, float* red, int& phase,
+                                         int nwarps, float (&mean)[NB], float (&rstd)[NB]) {
+    float s[NB];
 #pragma unroll
-    for (int e = 0; e < 8; e++) s[0] += x.v[e];
-    block_sum<1>(s, red, phase, nwarps);
-    mean = s[0] * inv_c;
-    float q[1] = {0.f};
+    for (int i = 0; i < NB; i++) {
+        s[i] = 0.f;
 #pragma unroll
-    for (int e = 0; e < 8; e++) {
-        const float d = active ? x.v[e] - mean : 0.f;  // padding threads (c0 >= C) must not add mean^2
-        q[0] += d * d;
+        for (int e = 0; e < 8; e++) s[i] += x[i].v[e];
     }
-    block_sum<1>(q, red, phase, nwarps);
-    rstd = rsqrtf(q[0] * inv_c + eps);
+    block_sum<NB>(s, red, phase, nwarps);
+    float q[NB];
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
+        mean[i] = s[i] * inv_c;
+        q[i] = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const float d = active ? x[i].v[e] - mean[i] : 0.f;  // padding threads (c0 >= C) must not add mean^2
+            q[i] += d * d;
+        }
+    }
+    block_sum<NB>(q, red, phase, nwarps);
+#pragma unroll
+    for (int i = 0; i < NB; i++) rstd[i] = rsqrtf(q[i] * inv_c + eps);
 }
 
 template <int NMIX>
@@ -61,43 +72,56 @@ __global__ void __launch_bounds__(256) ln_mix_fwd_kernel(const LnMixFwdArgs a) {
     const int row1 = min(row0 + LN_RUN, a.rows);
 
     auto normalize = [&](const F8& x, float mean, float rstd) {
+        if (!do_ln) return x;
         F8 h;
 #pragma unroll
         for (int e = 0; e < 8; e++) h.v[e] = rb((x.v[e] - mean) * rstd * g.v[e] + b.v[e]);
         return h;
     };
-    auto ln_or_id = [&](const F8& x, int row, bool write_stats) {
-        if (!do_ln) return x;
-        float mean, rstd;
-        ln_row(x, active, inv_c, a.eps, red, phase, nwarps, mean, rstd);
-        if (write_stats && tid == 0 && a.stats) {
-            a.stats[2 * row] = mean;
-            a.stats[2 * row + 1] = rstd;
-        }
-        return normalize(x, mean, rstd);
-    };
+    F8 cf[NMIX > 0 ? NMIX : 1];
+#pragma unroll
+    for (int m = 0; m < NMIX; m++) cf[m] = ldz(active, a.coef[m] + c0);
 
     F8 hprev = zero8();
     if (NMIX > 0 && row0 < a.rows && (row0 % a.T) != 0) {  // halo: LN of the row before the run
-        hprev = ln_or_id(ldz(active, a.x + (size_t)(row0 - 1) * a.C + c0), row0 - 1, false);
+        F8 xp[1] = {ldz(active, a.x + (size_t)(row0 - 1) * a.C + c0)};
+        float mean[1] = {0.f}, rstd[1] = {1.f};
+        if (do_ln) ln_stats<1>(xp, active, inv_c, a.eps, red, phase, nwarps, mean, rstd);
+        hprev = normalize(xp[0], mean[0], rstd[0]);
     }
-    for (int row = row0; row < row1; row++) {
-        const F8 h = ln_or_id(ldz(active, a.x + (size_t)row * a.C + c0), row, true);
-        if (a.h_out) stz(active, a.h_out + (size_t)row * a.C + c0, h);
-        if (NMIX > 0) {
-            if ((row % a.T) == 0) hprev = zero8();  // time_shift pads with zeros at t = 0
-            F8 xx;
+    for (int row = row0; row < row1; row += 4) {
+        F8 x[4];
 #pragma unroll
-            for (int e = 0; e < 8; e++) xx.v[e] = rb(hprev.v[e] - h.v[e]);
+        for (int i = 0; i < 4; i++) x[i] = ldz(active && row + i < row1, a.x + (size_t)(row + i) * a.C + c0);
+        float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {1.f, 1.f, 1.f, 1.f};
+        if (do_ln) {
+            ln_stats<4>(x, active, inv_c, a.eps, red, phase, nwarps, mean, rstd);
 #pragma unroll
-            for (int m = 0; m < NMIX; m++) {
-                const F8 c = ldz(active, a.coef[m] + c0);
-                F8 o;
+            for (int i = 0; i < 4; i++)
+                if (tid == i && row + i < row1 && a.stats) {
+                    a.stats[2 * (row + i)] = mean[i];
+                    a.stats[2 * (row + i) + 1] = rstd[i];
+                }
+        }
 #pragma unroll
-                for (int e = 0; e < 8; e++) o.v[e] = h.v[e] + rb(xx.v[e] * c.v[e]);
-                stz(active, a.out[m] + (size_t)row * a.C + c0, o);
+        for (int i = 0; i < 4; i++) {
+            if (row + i >= row1) break;
+            const F8 h = normalize(x[i], mean[i], rstd[i]);
+            if (a.h_out) stz(active, a.h_out + (size_t)(row + i) * a.C + c0, h);
+            if constexpr (NMIX > 0) {
+                if (((row + i) % a.T) == 0) hprev = zero8();  // time_shift pads with zeros at t = 0
+                F8 xx;
+#pragma unroll
+                for (int e = 0; e < 8; e++) xx.v[e] = rb(hprev.v[e] - h.v[e]);
+#pragma unroll
+                for (int m = 0; m < NMIX; m++) {
+                    F8 o;
+#pragma unroll
+                    for (int e = 0; e < 8; e++) o.v[e] = h.v[e] + rb(xx.v[e] * cf[m].v[e]);
+                    stz(active, a.out[m] + (size_t)(row + i) * a.C + c0, o);
+                }
+                hprev = h;
             }
-            hprev = h;
         }
     }
 }
@@ -138,6 +162,12 @@ __global__ void __launch_bounds__(256) ln_mix_bwd_kernel(const LnMixBwdArgs a) {
 #pragma unroll
     for (int m = 0; m < NMIX; m++) dco[m] = zero8();
 
+    struct Row {  // what is needed to finish a row once the gradient of its LN output is known
+        F8 xh, dh;
+        float rstd;
+        int row;
+        bool valid;
+    };
     auto xhat_of = [&](int row, F8& xh) {
         const F8 x = ldz(active, a.x + (size_t)row * a.C + c0);
         if (!do_ln) {
@@ -149,50 +179,59 @@ __global__ void __launch_bounds__(256) ln_mix_bwd_kernel(const LnMixBwdArgs a) {
         for (int e = 0; e < 8; e++) xh.v[e] = (x.v[e] - mean) * rstd;
         return rstd;
     };
-    // finishes row `row` given the gradient w.r.t. its LN output
-    auto finish = [&](int row, const F8& xh, float rstd, const F8& dh) {
-        float s[2] = {0.f, 0.f};
-        F8 dxh;
-        if (!do_ln) {
-            F8 dx = dh;
+    // LayerNorm backward of up to two rows with ONE block reduction (4 sums)
+    auto finish2 = [&](const Row& A, const Row& B) {
+        const Row* R[2] = {&A, &B};
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        F8 dxh[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            if (!R[i]->valid) continue;
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                dxh[i].v[e] = R[i]->dh.v[e] * g.v[e];
+                if (do_ln) {
+                    s[2 * i] += dxh[i].v[e];
+                    s[2 * i + 1] += dxh[i].v[e] * R[i]->xh.v[e];
+                    dgam.v[e] += R[i]->dh.v[e] * R[i]->xh.v[e];
+                    dbet.v[e] += R[i]->dh.v[e];
+                }
+            }
+        }
+        if (do_ln) block_sum<4>(s, red, phase, nwarps);
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            if (!R[i]->valid) continue;
+            F8 dx;
+            if (do_ln) {
+                const float m1 = s[2 * i] * inv_c, m2 = s[2 * i + 1] * inv_c;
+#pragma unroll
+                for (int e = 0; e < 8; e++) dx.v[e] = R[i]->rstd * (dxh[i].v[e] - m1 - R[i]->xh.v[e] * m2);
+            } else {
+                dx = R[i]->dh;
+            }
             if (a.dresid) {
-                const F8 r = ldz(active, a.dresid + (size_t)row * a.C + c0);
+                const F8 r = ldz(active, a.dresid + (size_t)R[i]->row * a.C + c0);
 #pragma unroll
                 for (int e = 0; e < 8; e++) dx.v[e] += r.v[e];
             }
-            stz(active, a.dx + (size_t)row * a.C + c0, dx);
-            return;
+            stz(active, a.dx + (size_t)R[i]->row * a.C + c0, dx);
         }
-#pragma unroll
-        for (int e = 0; e < 8; e++) {
-            dxh.v[e] = dh.v[e] * g.v[e];
-            s[0] += dxh.v[e];
-            s[1] += dxh.v[e] * xh.v[e];
-            dgam.v[e] += dh.v[e] * xh.v[e];
-            dbet.v[e] += dh.v[e];
-        }
-        block_sum<2>(s, red, phase, nwarps);
-        const float m1 = s[0] * inv_c, m2 = s[1] * inv_c;
-        F8 dx;
-#pragma unroll
-        for (int e = 0; e < 8; e++) dx.v[e] = rstd * (dxh.v[e] - m1 - xh.v[e] * m2);
-        if (a.dresid) {
-            const F8 r = ldz(active, a.dresid + (size_t)row * a.C + c0);
-#pragma unroll
-            for (int e = 0; e < 8; e++) dx.v[e] += r.v[e];
-        }
-        stz(active, a.dx + (size_t)row * a.C + c0, dx);
     };
 
     if constexpr (NMIX == 0) {
-        for (int row = row0; row < row1; row++) {
-            F8 xh;
-            const float rstd = xhat_of(row, xh);
-            finish(row, xh, rstd, ldz(active, a.dh + (size_t)row * a.C + c0));
+        for (int row = row0; row < row1; row += 2) {
+            Row A, B;
+            A.row = row; A.valid = true; A.rstd = xhat_of(row, A.xh); A.dh = ldz(active, a.dh + (size_t)row * a.C + c0);
+            B.row = row + 1; B.valid = row + 1 < row1;
+            if (B.valid) { B.rstd = xhat_of(row + 1, B.xh); B.dh = ldz(active, a.dh + (size_t)(row + 1) * a.C + c0); }
+            finish2(A, B);
         }
     } else {
-        // out_m[t] = h[t] + (h[t-1] - h[t]) c_m  =>  dh[t] = P[t] - Q[t] + Q[t+1],  P = sum_m dout_m, Q = sum_m dout_m c_m
-        F8 cf[NMIX > 0 ? NMIX : 1];
+        // out_m[t] = h[t] + (h[t-1] - h[t]) c_m  =>  dh[t] = P[t] - Q[t] + Q[t+1],  P = sum_m dout_m, Q = sum_m dout_m c_m.
+        // Rows are visited two at a time; a row is finished one iteration late, when Q of its successor is known, so each
+        // iteration finishes (previous pending row, first row of the pair) with one block reduction.
+        F8 cf[NMIX];
 #pragma unroll
         for (int m = 0; m < NMIX; m++) cf[m] = ldz(active, a.coef[m] + c0);
         F8 hprev = zero8();
@@ -202,24 +241,21 @@ __global__ void __launch_bounds__(256) ln_mix_bwd_kernel(const LnMixBwdArgs a) {
 #pragma unroll
             for (int e = 0; e < 8; e++) hprev.v[e] = rb(xh.v[e] * g.v[e] + b.v[e]);
         }
-        F8 Dp = zero8(), xhp = zero8();  // pending row: P - Q and its x-hat
-        float rstdp = 0.f;
-        bool pending = false;
-        for (int row = row0; row <= row1; row++) {
-            // row == row1 is the halo after the run: only its Q is needed (if it belongs to the same sequence)
-            const bool in_run = row < row1;
+        // P and Q of one row (and, for rows of the run, x-hat / rstd / the dcoef accumulation)
+        auto visit = [&](int row, bool in_run, F8& P, F8& Q, F8& xh, float& rstd) {
+            P = zero8(); Q = zero8();
             const bool exists = row < a.rows && (in_run || (row % a.T) != 0);
-            F8 P = zero8(), Q = zero8();
-            F8 xh, h, xx;
-            float rstd = 0.f;
+            F8 xx = zero8();
             if (in_run) {
                 rstd = xhat_of(row, xh);
                 if ((row % a.T) == 0) hprev = zero8();
+                F8 h;
 #pragma unroll
                 for (int e = 0; e < 8; e++) {
                     h.v[e] = rb(xh.v[e] * g.v[e] + b.v[e]);
                     xx.v[e] = rb(hprev.v[e] - h.v[e]);
                 }
+                hprev = h;
             }
             if (exists) {
 #pragma unroll
@@ -233,21 +269,47 @@ __global__ void __launch_bounds__(256) ln_mix_bwd_kernel(const LnMixBwdArgs a) {
                     }
                 }
             }
-            if (pending) {
-                F8 dh;
-                const bool same_seq = exists && (row % a.T) != 0;
+            return exists;
+        };
+        Row pend;
+        pend.valid = false;
+        F8 Dp = zero8();  // P - Q of the pending row
+        for (int row = row0; row < row1; row += 2) {
+            F8 P0, Q0, P1, Q1;
+            Row A, B;  // A: pending row (finished now), B: first row of the pair (finished now); second row becomes pending
+            float rstd1 = 1.f;
+            F8 xh1 = zero8();
+            B.row = row; B.valid = true;
+            visit(row, true, P0, Q0, B.xh, B.rstd);
+            const bool in1 = row + 1 < row1;
+            const bool ex1 = visit(row + 1, in1, P1, Q1, xh1, rstd1);
+            A = pend;
+            if (A.valid) {
+                const bool same = (row % a.T) != 0;
 #pragma unroll
-                for (int e = 0; e < 8; e++) dh.v[e] = Dp.v[e] + (same_seq ? Q.v[e] : 0.f);
-                finish(row - 1, xhp, rstdp, dh);
+                for (int e = 0; e < 8; e++) A.dh.v[e] = Dp.v[e] + (same ? Q0.v[e] : 0.f);
             }
-            if (in_run) {
+            const bool same1 = ex1 && ((row + 1) % a.T) != 0;
 #pragma unroll
-                for (int e = 0; e < 8; e++) Dp.v[e] = P.v[e] - Q.v[e];
-                xhp = xh;
-                rstdp = rstd;
-                hprev = h;
-                pending = true;
+            for (int e = 0; e < 8; e++) B.dh.v[e] = P0.v[e] - Q0.v[e] + (same1 ? Q1.v[e] : 0.f);
+            finish2(A, B);
+            pend.valid = in1;
+            if (in1) {
+                pend.row = row + 1; pend.xh = xh1; pend.rstd = rstd1;
+#pragma unroll
+                for (int e = 0; e < 8; e++) Dp.v[e] = P1.v[e] - Q1.v[e];
             }
+        }
+        if (pend.valid) {  // last row of the run: needs Q of the halo row after the run
+            F8 P, Q, xh;
+            float rstd;
+            const bool ex = visit(row1, false, P, Q, xh, rstd);
+            const bool same = ex && (row1 % a.T) != 0;
+#pragma unroll
+            for (int e = 0; e < 8; e++) pend.dh.v[e] = Dp.v[e] + (same ? Q.v[e] : 0.f);
+            Row none;
+            none.valid = false;
+            finish2(pend, none);
         }
     }
     if (!active) return;

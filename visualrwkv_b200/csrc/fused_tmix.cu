@@ -24,8 +24,9 @@ __device__ __forceinline__ float head_sum(float x) {  // over the 8 lanes (64 ch
     x += __shfl_xor_sync(0xffffffffu, x, 4);
     return x;
 }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
-__device__ __forceinline__ float softplusf_(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+// MUFU-based fast forms: their ~2 ulp fp32 error is far below the bf16 rounding applied right after
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float softplusf_(float x) { return x > 20.f ? x : __logf(1.f + __expf(x)); }
 
 // ------------------------------------------------------------------------------------------------------------
 // tmix_mid
@@ -48,9 +49,22 @@ __global__ void __launch_bounds__(256) tmix_mid_fwd_kernel(const TmixMidArgs a) 
     F8 v0 = zero8();
     if (a.has_vres) v0 = ldz(active, a.v0 + c0);
     const int row0 = blockIdx.x * TM_RUN, row1 = min(row0 + TM_RUN, a.rows);
+    // software pipeline: the loads of row+1 are issued before row is computed and stored
+    struct In { uint4 k, v, ww, aa, vf, vv; };
+    auto load = [&](int row) {
+        In r;
+        const size_t o = (size_t)row * a.C + c0;
+        const bool ok_ = active && row < row1;
+        r.k = ldraw(ok_, a.k + o); r.v = ldraw(ok_, a.v + o); r.ww = ldraw(ok_, a.ww + o); r.aa = ldraw(ok_, a.aa + o);
+        r.vf = ldraw(ok_ && a.has_vres, a.vfirst + o); r.vv = ldraw(ok_ && a.has_vres, a.vv + o);
+        return r;
+    };
+    In nxt = load(row0);
     for (int row = row0; row < row1; row++) {
         const size_t o = (size_t)row * a.C + c0;
-        const F8 k = ldz(active, a.k + o), v = ldz(active, a.v + o), ww = ldz(active, a.ww + o), aa = ldz(active, a.aa + o);
+        const In cur = nxt;
+        nxt = load(row + 1);
+        const F8 k = f8(cur.k), v = f8(cur.v), ww = f8(cur.ww), aa = f8(cur.aa);
         F8 ow, ok, ov, onkk, okka, u, av;
         float ss = 0.f;
 #pragma unroll
@@ -63,7 +77,7 @@ __global__ void __launch_bounds__(256) tmix_mid_fwd_kernel(const TmixMidArgs a) 
             ok.v[e] = k.v[e] * rb(1.f + rb(rb(av.v[e] - 1.f) * ka.v[e]));
         }
         if (a.has_vres) {
-            const F8 vf = ldz(active, a.vfirst + o), vv = ldz(active, a.vv + o);
+            const F8 vf = f8(cur.vf), vv = f8(cur.vv);
 #pragma unroll
             for (int e = 0; e < 8; e++) {
                 const float vg = rb(sigmoidf_(rb(v0.v[e] + vv.v[e])));
@@ -73,9 +87,10 @@ __global__ void __launch_bounds__(256) tmix_mid_fwd_kernel(const TmixMidArgs a) 
             ov = v;
         }
         const float nrm = fmaxf(rb(sqrtf(head_sum(ss))), 1e-12f);  // F.normalize(p=2, eps=1e-12)
+        const float inrm = 1.f / nrm;
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-            const float kk = rb(u.v[e] / nrm);
+            const float kk = rb(u.v[e] * inrm);
             onkk.v[e] = -kk;
             okka.v[e] = kk * av.v[e];
         }
@@ -92,11 +107,25 @@ __global__ void __launch_bounds__(256) tmix_mid_bwd_kernel(const TmixMidArgs a) 
     if (a.has_vres) v0 = ldz(active, a.v0 + c0);
     F8 gw0 = zero8(), ga0 = zero8(), gv0 = zero8(), gkk = zero8(), gka = zero8();
     const int row0 = blockIdx.x * TM_RUN, row1 = min(row0 + TM_RUN, a.rows);
+    struct In { uint4 k, ww, aa, dw, dk2, dv2, dnkk, dkka, v, vf, vv; };
+    auto load = [&](int row) {
+        In r;
+        const size_t o = (size_t)row * a.C + c0;
+        const bool ok_ = active && row < row1;
+        r.k = ldraw(ok_, a.k + o); r.ww = ldraw(ok_, a.ww + o); r.aa = ldraw(ok_, a.aa + o);
+        r.dw = ldraw(ok_, a.dw + o); r.dk2 = ldraw(ok_, a.dk2 + o); r.dv2 = ldraw(ok_, a.dv2 + o);
+        r.dnkk = ldraw(ok_, a.dnkk + o); r.dkka = ldraw(ok_, a.dkka + o);
+        const bool ov_ = ok_ && a.has_vres;
+        r.v = ldraw(ov_, a.v + o); r.vf = ldraw(ov_, a.vfirst + o); r.vv = ldraw(ov_, a.vv + o);
+        return r;
+    };
+    In nxt = load(row0);
     for (int row = row0; row < row1; row++) {
         const size_t o = (size_t)row * a.C + c0;
-        const F8 k = ldz(active, a.k + o), ww = ldz(active, a.ww + o), aa = ldz(active, a.aa + o);
-        const F8 dw = ldz(active, a.dw + o), dk2 = ldz(active, a.dk2 + o), dv2 = ldz(active, a.dv2 + o);
-        const F8 dnkk = ldz(active, a.dnkk + o), dkka = ldz(active, a.dkka + o);
+        const In cur = nxt;
+        nxt = load(row + 1);
+        const F8 k = f8(cur.k), ww = f8(cur.ww), aa = f8(cur.aa), dw = f8(cur.dw), dk2 = f8(cur.dk2), dv2 = f8(cur.dv2), dnkk = f8(cur.dnkk),
+                 dkka = f8(cur.dkka);
         F8 u, av, kk, dkk, odk, odww, odaa;
         float ss = 0.f;
 #pragma unroll
@@ -132,7 +161,7 @@ __global__ void __launch_bounds__(256) tmix_mid_bwd_kernel(const TmixMidArgs a) 
         }
         stz(active, a.dk + o, odk); stz(active, a.dww + o, odww); stz(active, a.daa + o, odaa);
         if (a.has_vres) {
-            const F8 v = ldz(active, a.v + o), vf = ldz(active, a.vfirst + o), vv = ldz(active, a.vv + o);
+            const F8 v = f8(cur.v), vf = f8(cur.vf), vv = f8(cur.vv);
             F8 odv, odvf, odvv;
 #pragma unroll
             for (int e = 0; e < 8; e++) {
@@ -176,10 +205,20 @@ __global__ void __launch_bounds__(256) tmix_post_fwd_kernel(const TmixPostArgs a
     const bool active = c0 < a.C;
     const F8 gm = ldz(active, a.gamma + c0), bt = ldz(active, a.beta + c0), rk = ldz(active, a.r_k + c0);
     const int row0 = blockIdx.x * TM_RUN, row1 = min(row0 + TM_RUN, a.rows);
+    struct In { uint4 y, r, k, v, g; };
+    auto load = [&](int row) {
+        In q;
+        const size_t o = (size_t)row * a.C + c0;
+        const bool ok_ = active && row < row1;
+        q.y = ldraw(ok_, a.y + o); q.r = ldraw(ok_, a.r + o); q.k = ldraw(ok_, a.k2 + o); q.v = ldraw(ok_, a.v2 + o); q.g = ldraw(ok_, a.g + o);
+        return q;
+    };
+    In nxt = load(row0);
     for (int row = row0; row < row1; row++) {
         const size_t o = (size_t)row * a.C + c0;
-        const F8 y = ldz(active, a.y + o), r = ldz(active, a.r + o), k = ldz(active, a.k2 + o), v = ldz(active, a.v2 + o),
-                 g = ldz(active, a.g + o);
+        const In cur = nxt;
+        nxt = load(row + 1);
+        const F8 y = f8(cur.y), r = f8(cur.r), k = f8(cur.k), v = f8(cur.v), g = f8(cur.g);
         float s1 = 0.f, sb = 0.f;
 #pragma unroll
         for (int e = 0; e < 8; e++) {
@@ -211,10 +250,21 @@ __global__ void __launch_bounds__(256) tmix_post_bwd_kernel(const TmixPostArgs a
     const F8 gm = ldz(active, a.gamma + c0), bt = ldz(active, a.beta + c0), rk = ldz(active, a.r_k + c0);
     F8 ggm = zero8(), gbt = zero8(), grk = zero8();
     const int row0 = blockIdx.x * TM_RUN, row1 = min(row0 + TM_RUN, a.rows);
+    struct In { uint4 y, r, k, v, g, dz; };
+    auto load = [&](int row) {
+        In q;
+        const size_t o = (size_t)row * a.C + c0;
+        const bool ok_ = active && row < row1;
+        q.y = ldraw(ok_, a.y + o); q.r = ldraw(ok_, a.r + o); q.k = ldraw(ok_, a.k2 + o); q.v = ldraw(ok_, a.v2 + o); q.g = ldraw(ok_, a.g + o);
+        q.dz = ldraw(ok_, a.dz + o);
+        return q;
+    };
+    In nxt = load(row0);
     for (int row = row0; row < row1; row++) {
         const size_t o = (size_t)row * a.C + c0;
-        const F8 y = ldz(active, a.y + o), r = ldz(active, a.r + o), k = ldz(active, a.k2 + o), v = ldz(active, a.v2 + o),
-                 g = ldz(active, a.g + o), dz = ldz(active, a.dz + o);
+        const In cur = nxt;
+        nxt = load(row + 1);
+        const F8 y = f8(cur.y), r = f8(cur.r), k = f8(cur.k), v = f8(cur.v), g = f8(cur.g), dz = f8(cur.dz);
         float s1 = 0.f, sb = 0.f;
 #pragma unroll
         for (int e = 0; e < 8; e++) {

@@ -43,6 +43,18 @@ __device__ __forceinline__ F8 ldz(bool active, const uint16_t* p) { return activ
 __device__ __forceinline__ void stz(bool active, uint16_t* p, const F8& r) {
     if (active) st_bf16x8(p, r);
 }
+// raw (still packed bf16) variants used by the software-pipelined row loops: half the registers of an F8
+__device__ __forceinline__ uint4 ldraw(bool active, const uint16_t* p) {
+    return active ? *reinterpret_cast<const uint4*>(p) : make_uint4(0u, 0u, 0u, 0u);
+}
+__device__ __forceinline__ F8 f8(const uint4 u) {
+    F8 r;
+    r.v[0] = bf16lo_to_f32(u.x); r.v[1] = bf16hi_to_f32(u.x);
+    r.v[2] = bf16lo_to_f32(u.y); r.v[3] = bf16hi_to_f32(u.y);
+    r.v[4] = bf16lo_to_f32(u.z); r.v[5] = bf16hi_to_f32(u.z);
+    r.v[6] = bf16lo_to_f32(u.w); r.v[7] = bf16hi_to_f32(u.w);
+    return r;
+}
 __host__ __device__ inline int row_threads(int C) { return ((C / 8 + 31) / 32) * 32; }
 // round-trip through bf16: what a bf16 eager op leaves in memory
 __device__ __forceinline__ float rb(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }

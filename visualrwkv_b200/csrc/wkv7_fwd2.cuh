@@ -294,8 +294,10 @@ wkv7_fwd2_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
             float x[1][R], z[1];
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                const u64 e = ffma2(a2[1], S[r][1], fmul2(a2[0], S[r][0]));
-                const u64 o = ffma2(a2[3], S[r][3], fmul2(a2[2], S[r][2]));
+                // same association as the fused next-sa dot inside step() (pairs 0,2 and 1,3): a sequence split at
+                // any point reproduces the one-shot run bit for bit
+                const u64 e = ffma2(S[r][2], a2[2], fmul2(S[r][0], a2[0]));
+                const u64 o = ffma2(S[r][3], a2[3], fmul2(S[r][1], a2[1]));
                 x[0][r] = hsum2(fadd2(e, o));
             }
             L.template reduce<1>(x, z);
