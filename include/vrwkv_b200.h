@@ -70,6 +70,71 @@ int vrwkv_wkv7_forward_state(int B, int T, int H, const uint16_t* w, const uint1
 /* Kernel-variant selection for benchmarking (0 = default heuristic). Thread-safe, process-wide. */
 int vrwkv_wkv7_set_variant(int fwd_variant, int bwd_variant);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Fused row-wise kernels of the RWKV-7 block (all tensors bf16 row-major [rows, C], rows = B*T,
+ * C a multiple of 64 and <= 2048; per-channel parameters bf16 [C]).  Parameter gradients leave as
+ * fp32 per-CTA partial rows `partial[blocks][n][C]` that the caller sums over `blocks`
+ * (blocks = vrwkv_ln_mix_blocks(rows) / vrwkv_tmix_blocks(rows)).
+ * ------------------------------------------------------------------------------------------ */
+
+/* LayerNorm (+ token shift + NMIX lerps) — replaces ln1/ln2 + nn.ZeroPad2d((0,0,1,-1)) + the six / one
+ * `x + xx * x_*` mixes (v7.00/src/model.py:149,166-173,222-224,250,252) and the plain LayerNorms (:248,323,338).
+ * nmix in {0,1,6}; gamma == beta == NULL: input already normalised (mix only); out[m] = h + (shift(h) - h) coef[m].
+ * coef / out / dout are HOST arrays of nmix device pointers.  stats: f32 [rows,2] (mean, rstd). */
+int vrwkv_ln_mix_blocks(int rows);
+int vrwkv_ln_mix_forward(int rows, int T, int C, int nmix, float eps, const uint16_t* x, const uint16_t* gamma,
+                         const uint16_t* beta, const uint16_t* const* coef, uint16_t* const* out, uint16_t* h_out,
+                         float* stats, void* stream);
+/* dx = LN-backward(sum over mixes) [+ dresid]; partial rows: dgamma, dbeta, dcoef[0..nmix). dh: gradient of the LN
+ * output when nmix == 0. */
+int vrwkv_ln_mix_backward(int rows, int T, int C, int nmix, const uint16_t* x, const float* stats, const uint16_t* gamma,
+                          const uint16_t* beta, const uint16_t* const* coef, const uint16_t* const* dout,
+                          const uint16_t* dh, const uint16_t* dresid, uint16_t* dx, float* partial, void* stream);
+
+/* tmix_mid — model.py:176-190: w = -softplus(-(w0+ww)) - 0.5 ; a = sigmoid(a0+aa) ; v2 = v + (vfirst - v) sigmoid(v0+vv)
+ * (vfirst == NULL for layer 0: v2 = v) ; kk = normalize_head(k*k_k) ; k2 = k (1 + (a-1) k_a) ; nkk = -kk ; kka = kk*a. */
+int vrwkv_tmix_blocks(int rows);
+int vrwkv_tmix_mid_forward(int rows, int C, const uint16_t* k, const uint16_t* v, const uint16_t* vfirst, const uint16_t* ww,
+                           const uint16_t* aa, const uint16_t* vv, const uint16_t* w0, const uint16_t* a0, const uint16_t* v0,
+                           const uint16_t* k_k, const uint16_t* k_a, uint16_t* w, uint16_t* k2, uint16_t* v2, uint16_t* nkk,
+                           uint16_t* kka, void* stream);
+/* partial rows: dw0, da0, dv0, dk_k, dk_a */
+int vrwkv_tmix_mid_backward(int rows, int C, const uint16_t* k, const uint16_t* v, const uint16_t* vfirst, const uint16_t* ww,
+                            const uint16_t* aa, const uint16_t* vv, const uint16_t* w0, const uint16_t* a0, const uint16_t* v0,
+                            const uint16_t* k_k, const uint16_t* k_a, const uint16_t* dw, const uint16_t* dk2,
+                            const uint16_t* dv2, const uint16_t* dnkk, const uint16_t* dkka, uint16_t* dk, uint16_t* dv,
+                            uint16_t* dvfirst, uint16_t* dww, uint16_t* daa, uint16_t* dvv, float* partial, void* stream);
+
+/* tmix_post — model.py:191-194: z = (GroupNorm_H(y; eps) + (sum_head r k2 r_k) v2) * g   (the input of `output`). */
+int vrwkv_tmix_post_forward(int rows, int C, float eps, const uint16_t* y, const uint16_t* r, const uint16_t* k2,
+                            const uint16_t* v2, const uint16_t* g, const uint16_t* gamma, const uint16_t* beta,
+                            const uint16_t* r_k, uint16_t* z, void* stream);
+/* partial rows: dgamma, dbeta, dr_k */
+int vrwkv_tmix_post_backward(int rows, int C, float eps, const uint16_t* y, const uint16_t* r, const uint16_t* k2,
+                             const uint16_t* v2, const uint16_t* g, const uint16_t* gamma, const uint16_t* beta,
+                             const uint16_t* r_k, const uint16_t* dz, uint16_t* dy, uint16_t* dr, uint16_t* dk2, uint16_t* dv2,
+                             uint16_t* dg, float* partial, void* stream);
+
+/* relu(x)^2 — model.py:225 (n elements, n % 8 == 0). The *_from_act backward needs only y = relu(x)^2. */
+int vrwkv_relu_sq_forward(size_t n, const uint16_t* x, uint16_t* y, void* stream);
+int vrwkv_relu_sq_backward(size_t n, const uint16_t* x, const uint16_t* dy, uint16_t* dx, void* stream);
+int vrwkv_relu_sq_backward_from_act(size_t n, const uint16_t* y, const uint16_t* dy, uint16_t* dx, void* stream);
+
+/* Shifted cross-entropy + L2Wrap over logits [rows = B*T, V] (bf16) — model.py:418-434, 257-271.
+ * forward: lse/rowmax/nll f32 [rows], argmax i32 [rows]; the target of row (b,t) is labels[b,t+1] (int64 [B,T]).
+ * backward: overwrites `logits_inout` with wrow[row] * (softmax - onehot(target)) + l2 * rowmax * onehot(argmax). */
+int vrwkv_ce_forward(int rows, int T, int V, int ignore_index, const uint16_t* logits, const long long* labels, float* lse,
+                     float* rowmax, int* argmax, float* nll, void* stream);
+int vrwkv_ce_backward(int rows, int T, int V, int ignore_index, uint16_t* logits_inout, const long long* labels,
+                      const float* lse, const float* rowmax, const int* argmax, const float* wrow, float l2, void* stream);
+
+/* bf16 GEMM on the tcgen05 tensor cores: C[M,N] = epilogue(A[M,K] . B[N,K]^T), fp32 accumulate in TMEM.
+ * epilogue 0: none (receptance/key/value, model.py:175-178); 1: relu(.)^2 (channel-mix key, :225);
+ * 2: + R[M,N] (output / value projections with the residual add, :194,227,251-252).  K % 64 == 0, N % 128 == 0. */
+int vrwkv_gemm_bf16_tn(int M, int N, int K, const uint16_t* A, const uint16_t* B, uint16_t* C, int epilogue,
+                       const uint16_t* R, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

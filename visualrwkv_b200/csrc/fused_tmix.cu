@@ -342,6 +342,18 @@ __global__ void __launch_bounds__(256) relu_sq_bwd_kernel(const uint16_t* x, con
     }
 }
 
+// backward of relu(x)^2 from the ACTIVATION y = relu(x)^2 alone (the tcgen05 GEMM epilogue emits y and never
+// materialises x): d/dx = 2 relu(x) = 2 sqrt(y)
+__global__ void __launch_bounds__(256) relu_sq_bwd_from_act_kernel(const uint16_t* y, const uint16_t* dy, uint16_t* dx, size_t n8) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const F8 v = ld_bf16x8(y + i * 8), d = ld_bf16x8(dy + i * 8);
+        F8 o;
+#pragma unroll
+        for (int e = 0; e < 8; e++) o.v[e] = 2.f * sqrtf(v.v[e]) * d.v[e];
+        st_bf16x8(dx + i * 8, o);
+    }
+}
+
 }  // namespace vrwkv
 
 using namespace vrwkv;
@@ -439,6 +451,14 @@ extern "C" int vrwkv_relu_sq_forward(size_t n, const uint16_t* x, uint16_t* y, v
 extern "C" int vrwkv_relu_sq_backward(size_t n, const uint16_t* x, const uint16_t* dy, uint16_t* dx, void* stream) {
     if (!x || !dy || !dx || (n % 8)) return vrwkv_fail(VRWKV_EINVAL, "relu_sq_backward: null pointer or n %% 8 != 0");
     relu_sq_bwd_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(x, dy, dx, n / 8);
+    VRWKV_CUDA(cudaGetLastError());
+    vrwkv_count_launch(1);
+    return VRWKV_OK;
+}
+
+extern "C" int vrwkv_relu_sq_backward_from_act(size_t n, const uint16_t* y, const uint16_t* dy, uint16_t* dx, void* stream) {
+    if (!y || !dy || !dx || (n % 8)) return vrwkv_fail(VRWKV_EINVAL, "relu_sq_backward_from_act: null pointer or n %% 8 != 0");
+    relu_sq_bwd_from_act_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(y, dy, dx, n / 8);
     VRWKV_CUDA(cudaGetLastError());
     vrwkv_count_launch(1);
     return VRWKV_OK;

@@ -142,6 +142,15 @@ def relu_sq_backward(x, dy):
     return dx
 
 
+def relu_sq_backward_from_act(act, dy):
+    L = _lib.lib()
+    _bf16c(act, dy)
+    dx = torch.empty_like(act)
+    _chk(L.vrwkv_relu_sq_backward_from_act(_c_size_t(act.numel()), _p(act), _p(dy), _p(dx), _lib.cur_stream()),
+         "vrwkv_relu_sq_backward_from_act")
+    return dx
+
+
 def wkv7_fwd_raw(w, q, k, v, a, b):
     """[B,T,H,64] bf16 x6 -> y, s, sa through torch.ops.wind_backstepping (timed when wkv7.PROFILE is set)."""
     _lib.load_torch_ops()
@@ -220,7 +229,10 @@ class TmixBlockFn(torch.autograd.Function):
         v4 = lambda t: t.view(B, T, H, 64)
         y, s, sa = wkv7_fwd_raw(v4(w), v4(r), v4(k2), v4(v2_), v4(nkk), v4(kka))
         z = tmix_post_forward(y.view(rows, C), r, k2, v2_, g, lnx_w, lnx_b, r_k.reshape(C), gn_eps)
-        out = torch.addmm(x2, z, Wo.t()) if with_ln else z @ Wo.t()
+        if gemm_supported(rows, C, C):
+            out = gemm_tn(z, Wo, EPI_ADD, x2) if with_ln else gemm_tn(z, Wo, EPI_NONE)
+        else:
+            out = torch.addmm(x2, z, Wo.t()) if with_ln else z @ Wo.t()
         ctx.save_for_backward(x2, stats, ln_w, ln_b, *coefs, xr, xw, xk, xv, xa, xg, r, k, v, hw, ww, ha, aa, hg, g, hv, vv, vf2,
                               w, k2, v2_, nkk, kka, y, s, sa, z, w0, w1, w2, a0, a1, a2, v0, v1, v2, g1, g2, k_k, k_a, r_k,
                               Wr, Wk, Wv, Wo, lnx_w, lnx_b)
@@ -306,9 +318,17 @@ class CmixBlockFn(torch.autograd.Function):
         x2 = x.reshape(rows, C).contiguous()
         ck = x_k.reshape(C)
         (xk,), _, stats = ln_mix_forward(x2, T, ln_w if with_ln else None, ln_b if with_ln else None, ln_eps, [ck])
-        hk = xk @ Wkey.t()
-        act = relu_sq_forward(hk)
-        out = torch.addmm(x2, act, Wval.t()) if with_ln else act @ Wval.t()
+        M, Hd = rows, Wkey.shape[0]
+        if gemm_supported(M, Hd, C) and gemm_supported(M, C, Hd):
+            # key GEMM with relu^2 in the tcgen05 epilogue (the 4C-wide pre-activation never touches HBM), value GEMM
+            # with the residual add in the epilogue
+            act = gemm_tn(xk, Wkey, EPI_RELU_SQ)
+            out = gemm_tn(act, Wval, EPI_ADD, x2) if with_ln else gemm_tn(act, Wval, EPI_NONE)
+            hk = None
+        else:
+            hk = xk @ Wkey.t()
+            act = relu_sq_forward(hk)
+            out = torch.addmm(x2, act, Wval.t()) if with_ln else act @ Wval.t()
         ctx.save_for_backward(x2, stats, ln_w, ln_b, ck, xk, hk, act, Wkey, Wval)
         ctx.meta = (B, T, C, with_ln)
         return out.view(B, T, C)
@@ -320,7 +340,7 @@ class CmixBlockFn(torch.autograd.Function):
         do = dout.reshape(B * T, C).contiguous()
         dact = do @ Wval
         dWval = do.t() @ act
-        dhk = relu_sq_backward(hk, dact)
+        dhk = relu_sq_backward(hk, dact) if hk is not None else relu_sq_backward_from_act(act, dact)
         dxk = dhk @ Wkey
         dWkey = dhk.t() @ xk
         dx, dlnw, dlnb, dco = ln_mix_backward(x2, T, stats, ln_w if with_ln else None, ln_b if with_ln else None, [ck], [dxk],
@@ -379,3 +399,26 @@ class HeadLossFn(torch.autograd.Function):
         dx = dlogits @ weight
         dW = dlogits.t() @ x2
         return dx.view(B, T, C), dW, None, None
+
+
+# ------------------------------------------------------------------------------------------------------
+# tcgen05 GEMM with fused epilogues (csrc/gemm_sm100.cu)
+# ------------------------------------------------------------------------------------------------------
+EPI_NONE, EPI_RELU_SQ, EPI_ADD = 0, 1, 2
+
+
+def gemm_tn(a, w, epilogue=EPI_NONE, residual=None):
+    """C[M,N] = epilogue(a[M,K] @ w[N,K]^T) on the tcgen05 tensor cores (bf16 in, fp32 accumulate, bf16 out)."""
+    L = _lib.lib()
+    _bf16c(a, w, residual)
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    c = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    _chk(L.vrwkv_gemm_bf16_tn(_c_int(M), _c_int(N), _c_int(K), _p(a), _p(w), _p(c), _c_int(epilogue), _p(residual),
+                              _lib.cur_stream()), "vrwkv_gemm_bf16_tn")
+    return c
+
+
+def gemm_supported(M, N, K):
+    return K % 64 == 0 and N % 128 == 0 and M > 0
