@@ -126,8 +126,8 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--golden", action="store_true")
     ap.add_argument("--time", action="store_true")
-    ap.add_argument("--fv", default="1,2,3,4,5")
-    ap.add_argument("--bv", default="1,2,3")
+    ap.add_argument("--fv", default="1,2")
+    ap.add_argument("--bv", default="1,2")
     args = ap.parse_args()
     _lib.load_torch_ops()
     fvs = [int(x) for x in args.fv.split(",")]

@@ -21,7 +21,6 @@
 // (b,t,c) element; the reference contract adds 4 B (sa) + 16 B (s) of reads.
 #pragma once
 #include "common.cuh"
-#include "wkv7_bwd.cuh"
 #include "wkv7_fwd2.cuh"
 
 namespace vrwkv {
@@ -41,7 +40,7 @@ struct alignas(128) Wkv7Bwd2Smem {
 // consecutive indices) are 16-byte chunks that are contiguous across lanes.
 __device__ __forceinline__ int perm_col(int j) { return ((j >> 2) & 1) * 32 + 4 * (j >> 3) + (j & 3); }
 
-template <int R, int NSTAGE>
+template <int R, int NSTAGE, int UNROLL = 2>
 __global__ void __launch_bounds__((WKV_N / R) * 8 + 32)
 wkv7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_q,
                  const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
@@ -321,7 +320,7 @@ wkv7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         mbar_wait(&sm.full_f[buf], (n >> 1) & 1);
         __syncwarp();
         const size_t ind0 = (((size_t)bb * T + (size_t)c * TC) * H + hh) * N;
-#pragma unroll 2
+#pragma unroll UNROLL
         for (int t = TC - 1; t >= 0; t--) step(stage, buf, t, ind0 + (size_t)t * H * N);
         __syncwarp();
         if (lane == 0) {

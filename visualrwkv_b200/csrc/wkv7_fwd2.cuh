@@ -116,7 +116,7 @@ struct RowLanes {
     }
 };
 
-template <int R, int NSTAGE>
+template <int R, int NSTAGE, int UNROLL = 5>
 __global__ void __launch_bounds__((WKV_N / R) * 8 + 32)
 wkv7_fwd2_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_q,
                  const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
@@ -305,7 +305,7 @@ wkv7_fwd2_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
             L.allgather(z[0], sa);
         }
         if (nsteps == TC) {
-#pragma unroll 5
+#pragma unroll UNROLL
             for (int t = 0; t < TC - 1; t++) step(stage, buf, t, ind0 + (size_t)t * H * N, true);
             step(stage, buf, TC - 1, ind0 + (size_t)(TC - 1) * H * N, false);
             if (p.s) {  // transposed checkpoint: s[b,h,c,j,i] = S_ij  (wkv7_cuda.cu:44-50)

@@ -9,7 +9,6 @@
 
 #include "../../include/vrwkv_b200.h"
 #include "host_util.h"
-#include "wkv7_bwd.cuh"
 #include "wkv7_fwd.cuh"
 #include "wkv7_bwd2.cuh"
 #include "wkv7_fwd2.cuh"
@@ -31,41 +30,9 @@ static int make_stream_map(CUtensorMap* m, const void* base, int B, int T, int H
                            WKV_TC, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
-template <int L, int R, int NCONV, int NSTAGE>
-static int launch_fwd(const CUtensorMap* tm, const Wkv7FwdArgs& a, cudaStream_t st) {
-    auto kern = wkv7_fwd_kernel<L, R, NCONV, NSTAGE>;
-    const size_t smem = sizeof(Wkv7FwdSmem<NSTAGE>) + 128;
-    static std::atomic<bool> configured{false};
-    if (!configured.load()) {
-        VRWKV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured.store(true);
-    }
-    dim3 grid(a.H, a.B), block((WKV_N / R) * L + NCONV * 32);
-    kern<<<grid, block, smem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], a);
-    VRWKV_CUDA(cudaGetLastError());
-    vrwkv_count_launch(1);
-    return VRWKV_OK;
-}
-
-template <int L, int NCONV, int NSTAGE>
-static int launch_bwd(const CUtensorMap* tm, const Wkv7BwdArgs& a, cudaStream_t st) {
-    auto kern = wkv7_bwd_kernel<L, NCONV, NSTAGE>;
-    const size_t smem = sizeof(Wkv7BwdSmem<NSTAGE>) + 128;
-    static std::atomic<bool> configured{false};
-    if (!configured.load()) {
-        VRWKV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured.store(true);
-    }
-    dim3 grid(a.H, a.B), block(WKV_N * L + NCONV * 32);
-    kern<<<grid, block, smem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], tm[7], a);
-    VRWKV_CUDA(cudaGetLastError());
-    vrwkv_count_launch(1);
-    return VRWKV_OK;
-}
-
-template <int R, int NSTAGE>
+template <int R, int NSTAGE, int UNROLL = 5>
 static int launch_fwd2(const CUtensorMap* tm, const Wkv7FwdArgs& a, cudaStream_t st) {
-    auto kern = wkv7_fwd2_kernel<R, NSTAGE>;
+    auto kern = wkv7_fwd2_kernel<R, NSTAGE, UNROLL>;
     const size_t smem = sizeof(Wkv7Fwd2Smem<NSTAGE>) + 128;
     VRWKV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(a.H, a.B), block((WKV_N / R) * 8 + 32);
@@ -75,9 +42,9 @@ static int launch_fwd2(const CUtensorMap* tm, const Wkv7FwdArgs& a, cudaStream_t
     return VRWKV_OK;
 }
 
-template <int R, int NSTAGE>
+template <int R, int NSTAGE, int UNROLL = 2>
 static int launch_bwd2(const CUtensorMap* tm, const Wkv7BwdArgs& a, cudaStream_t st) {
-    auto kern = wkv7_bwd2_kernel<R, NSTAGE>;
+    auto kern = wkv7_bwd2_kernel<R, NSTAGE, UNROLL>;
     const size_t smem = sizeof(Wkv7Bwd2Smem<NSTAGE>) + 128;
     VRWKV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(a.H, a.B), block((WKV_N / R) * 8 + 32);
@@ -114,15 +81,10 @@ extern "C" int vrwkv_wkv7_forward_state(int B, int T, int H, const uint16_t* w, 
     Wkv7FwdArgs args{B, T, H, y, s, sa, state_in, state_out};
     cudaStream_t st = (cudaStream_t)stream;
     int var = g_fwd_variant.load();
-    if (var == 0) var = 6;
+    if (var == 0) var = 1;
     switch (var) {
-        case 1: return launch_fwd<4, 2, 4, 4>(tm, args, st);
-        case 2: return launch_fwd<2, 1, 4, 4>(tm, args, st);
-        case 3: return launch_fwd<4, 1, 4, 4>(tm, args, st);
-        case 4: return launch_fwd<8, 1, 4, 4>(tm, args, st);
-        case 5: return launch_fwd<8, 2, 4, 4>(tm, args, st);
-        case 6: return launch_fwd2<4, 4>(tm, args, st);
-        case 7: return launch_fwd2<2, 4>(tm, args, st);
+        case 1: return launch_fwd2<4, 4>(tm, args, st);  // 4 rows x 8 columns per thread, 4 compute warps
+        case 2: return launch_fwd2<2, 4>(tm, args, st);  // 2 rows x 8 columns per thread, 8 compute warps
         default: return vrwkv_fail(VRWKV_EINVAL, "wkv7 forward: unknown variant %d", var);
     }
 }
@@ -151,13 +113,10 @@ extern "C" int vrwkv_wkv7_backward(int B, int T, int H, const uint16_t* w, const
     Wkv7BwdArgs args{B, T, H, s, dw, dq, dk, dv, da, db};
     cudaStream_t st = (cudaStream_t)stream;
     int var = g_bwd_variant.load();
-    if (var == 0) var = 4;
+    if (var == 0) var = 1;
     switch (var) {
-        case 1: return launch_bwd<4, 4, 3>(tm, args, st);
-        case 2: return launch_bwd<2, 4, 3>(tm, args, st);
-        case 3: return launch_bwd<8, 4, 3>(tm, args, st);
-        case 4: return launch_bwd2<4, 3>(tm, args, st);
-        case 5: return launch_bwd2<2, 3>(tm, args, st);
+        case 1: return launch_bwd2<4, 3>(tm, args, st);
+        case 2: return launch_bwd2<2, 3>(tm, args, st);
         default: return vrwkv_fail(VRWKV_EINVAL, "wkv7 backward: unknown variant %d", var);
     }
 }
