@@ -99,12 +99,13 @@ int vrwkv_tmix_mid_forward(int rows, int C, const uint16_t* k, const uint16_t* v
                            const uint16_t* aa, const uint16_t* vv, const uint16_t* w0, const uint16_t* a0, const uint16_t* v0,
                            const uint16_t* k_k, const uint16_t* k_a, uint16_t* w, uint16_t* k2, uint16_t* v2, uint16_t* nkk,
                            uint16_t* kka, void* stream);
-/* partial rows: dw0, da0, dv0, dk_k, dk_a */
+/* partial rows: dw0, da0, dv0, dk_k, dk_a.  dk2b / dv2b: optional second gradient contributions (added to dk2 / dv2). */
 int vrwkv_tmix_mid_backward(int rows, int C, const uint16_t* k, const uint16_t* v, const uint16_t* vfirst, const uint16_t* ww,
                             const uint16_t* aa, const uint16_t* vv, const uint16_t* w0, const uint16_t* a0, const uint16_t* v0,
                             const uint16_t* k_k, const uint16_t* k_a, const uint16_t* dw, const uint16_t* dk2,
-                            const uint16_t* dv2, const uint16_t* dnkk, const uint16_t* dkka, uint16_t* dk, uint16_t* dv,
-                            uint16_t* dvfirst, uint16_t* dww, uint16_t* daa, uint16_t* dvv, float* partial, void* stream);
+                            const uint16_t* dv2, const uint16_t* dnkk, const uint16_t* dkka, const uint16_t* dk2b,
+                            const uint16_t* dv2b, uint16_t* dk, uint16_t* dv, uint16_t* dvfirst, uint16_t* dww, uint16_t* daa,
+                            uint16_t* dvv, float* partial, void* stream);
 
 /* tmix_post — model.py:191-194: z = (GroupNorm_H(y; eps) + (sum_head r k2 r_k) v2) * g   (the input of `output`). */
 int vrwkv_tmix_post_forward(int rows, int C, float eps, const uint16_t* y, const uint16_t* r, const uint16_t* k2,
@@ -115,6 +116,9 @@ int vrwkv_tmix_post_backward(int rows, int C, float eps, const uint16_t* y, cons
                              const uint16_t* v2, const uint16_t* g, const uint16_t* gamma, const uint16_t* beta,
                              const uint16_t* r_k, const uint16_t* dz, uint16_t* dy, uint16_t* dr, uint16_t* dk2, uint16_t* dv2,
                              uint16_t* dg, float* partial, void* stream);
+
+/* out[n*C] (bf16) = sum_b partial[b][n*C]: second stage of the parameter gradients of the kernels above. */
+int vrwkv_reduce_partials(int nblocks, int n_times_c, const float* partial, uint16_t* out, void* stream);
 
 /* relu(x)^2 — model.py:225 (n elements, n % 8 == 0). The *_from_act backward needs only y = relu(x)^2. */
 int vrwkv_relu_sq_forward(size_t n, const uint16_t* x, uint16_t* y, void* stream);

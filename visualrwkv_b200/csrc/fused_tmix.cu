@@ -38,6 +38,7 @@ struct TmixMidArgs {
     uint16_t *w, *k2, *v2, *nkk, *kka;                   // forward outputs
     // backward
     const uint16_t *dw, *dk2, *dv2, *dnkk, *dkka;
+    const uint16_t *dk2b, *dv2b;  // optional second contributions to dk2 / dv2 (summed here)
     uint16_t *dk, *dv, *dvfirst, *dww, *daa, *dvv;
     float* partial;  // [grid][5][C]: dw0, da0, dv0, dk_k, dk_a
 };
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(256) tmix_mid_bwd_kernel(const TmixMidArgs a) 
     if (a.has_vres) v0 = ldz(active, a.v0 + c0);
     F8 gw0 = zero8(), ga0 = zero8(), gv0 = zero8(), gkk = zero8(), gka = zero8();
     const int row0 = blockIdx.x * TM_RUN, row1 = min(row0 + TM_RUN, a.rows);
-    struct In { uint4 k, ww, aa, dw, dk2, dv2, dnkk, dkka, v, vf, vv; };
+    struct In { uint4 k, ww, aa, dw, dk2, dv2, dnkk, dkka, v, vf, vv, dk2b, dv2b; };
     auto load = [&](int row) {
         In r;
         const size_t o = (size_t)row * a.C + c0;
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(256) tmix_mid_bwd_kernel(const TmixMidArgs a) 
         r.k = ldraw(ok_, a.k + o); r.ww = ldraw(ok_, a.ww + o); r.aa = ldraw(ok_, a.aa + o);
         r.dw = ldraw(ok_, a.dw + o); r.dk2 = ldraw(ok_, a.dk2 + o); r.dv2 = ldraw(ok_, a.dv2 + o);
         r.dnkk = ldraw(ok_, a.dnkk + o); r.dkka = ldraw(ok_, a.dkka + o);
+        r.dk2b = ldraw(ok_ && a.dk2b != nullptr, a.dk2b + o); r.dv2b = ldraw(ok_ && a.dv2b != nullptr, a.dv2b + o);
         const bool ov_ = ok_ && a.has_vres;
         r.v = ldraw(ov_, a.v + o); r.vf = ldraw(ov_, a.vfirst + o); r.vv = ldraw(ov_, a.vv + o);
         return r;
@@ -124,8 +126,16 @@ __global__ void __launch_bounds__(256) tmix_mid_bwd_kernel(const TmixMidArgs a) 
         const size_t o = (size_t)row * a.C + c0;
         const In cur = nxt;
         nxt = load(row + 1);
-        const F8 k = f8(cur.k), ww = f8(cur.ww), aa = f8(cur.aa), dw = f8(cur.dw), dk2 = f8(cur.dk2), dv2 = f8(cur.dv2), dnkk = f8(cur.dnkk),
-                 dkka = f8(cur.dkka);
+        const F8 k = f8(cur.k), ww = f8(cur.ww), aa = f8(cur.aa), dw = f8(cur.dw), dnkk = f8(cur.dnkk), dkka = f8(cur.dkka);
+        F8 dk2 = f8(cur.dk2), dv2 = f8(cur.dv2);
+        {
+            const F8 kb = f8(cur.dk2b), vb = f8(cur.dv2b);  // zeros when absent
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                dk2.v[e] += kb.v[e];
+                dv2.v[e] += vb.v[e];
+            }
+        }
         F8 u, av, kk, dkk, odk, odww, odaa;
         float ss = 0.f;
 #pragma unroll
@@ -354,6 +364,44 @@ __global__ void __launch_bounds__(256) relu_sq_bwd_from_act_kernel(const uint16_
     }
 }
 
+// second stage of the per-channel parameter gradients: out[i] (bf16) = sum over blocks of partial[blk][i], i in [0, n*C).
+// CTA = 64 column groups (4 consecutive columns each, float4 loads) x 4 slices of the block range; the slices are
+// combined through shared memory.  ~100 CTAs, every load coalesced: the 6-25 MB of partials stream in a few microseconds.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* partial, uint16_t* out, int nb, int nc) {
+    __shared__ float4 red[4][64];
+    const int cg = threadIdx.x & 63, slice = threadIdx.x >> 6;
+    const int col = (blockIdx.x * 64 + cg) * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < nc) {
+        float4 s2 = make_float4(0.f, 0.f, 0.f, 0.f);
+        int b = slice;
+        for (; b + 4 < nb; b += 8) {
+            const float4 x = *reinterpret_cast<const float4*>(partial + (size_t)b * nc + col);
+            const float4 y = *reinterpret_cast<const float4*>(partial + (size_t)(b + 4) * nc + col);
+            s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+            s2.x += y.x; s2.y += y.y; s2.z += y.z; s2.w += y.w;
+        }
+        for (; b < nb; b += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(partial + (size_t)b * nc + col);
+            s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+        }
+        s.x += s2.x; s.y += s2.y; s.z += s2.z; s.w += s2.w;
+    }
+    red[slice][cg] = s;
+    __syncthreads();
+    if (slice == 0 && col < nc) {
+        float4 t = red[0][cg];
+#pragma unroll
+        for (int k = 1; k < 4; k++) {
+            t.x += red[k][cg].x; t.y += red[k][cg].y; t.z += red[k][cg].z; t.w += red[k][cg].w;
+        }
+        uint2 o;
+        o.x = pack_bf16x2(t.x, t.y);
+        o.y = pack_bf16x2(t.z, t.w);
+        *reinterpret_cast<uint2*>(out + col) = o;
+    }
+}
+
 }  // namespace vrwkv
 
 using namespace vrwkv;
@@ -389,15 +437,15 @@ extern "C" int vrwkv_tmix_mid_backward(int rows, int C, const uint16_t* k, const
                                        const uint16_t* ww, const uint16_t* aa, const uint16_t* vv, const uint16_t* w0,
                                        const uint16_t* a0, const uint16_t* v0, const uint16_t* k_k, const uint16_t* k_a,
                                        const uint16_t* dw, const uint16_t* dk2, const uint16_t* dv2, const uint16_t* dnkk,
-                                       const uint16_t* dkka, uint16_t* dk, uint16_t* dv, uint16_t* dvfirst, uint16_t* dww,
-                                       uint16_t* daa, uint16_t* dvv, float* partial, void* stream) {
+                                       const uint16_t* dkka, const uint16_t* dk2b, const uint16_t* dv2b, uint16_t* dk, uint16_t* dv,
+                                       uint16_t* dvfirst, uint16_t* dww, uint16_t* daa, uint16_t* dvv, float* partial, void* stream) {
     int rc = tm_check(rows, C, "tmix_mid_backward");
     if (rc) return rc;
     TmixMidArgs a{};
     a.rows = rows; a.C = C; a.has_vres = vfirst != nullptr;
     a.k = k; a.v = v; a.vfirst = vfirst; a.ww = ww; a.aa = aa; a.vv = vv;
     a.w0 = w0; a.a0 = a0; a.v0 = v0; a.k_k = k_k; a.k_a = k_a;
-    a.dw = dw; a.dk2 = dk2; a.dv2 = dv2; a.dnkk = dnkk; a.dkka = dkka;
+    a.dw = dw; a.dk2 = dk2; a.dv2 = dv2; a.dnkk = dnkk; a.dkka = dkka; a.dk2b = dk2b; a.dv2b = dv2b;
     a.dk = dk; a.dv = dv; a.dvfirst = dvfirst; a.dww = dww; a.daa = daa; a.dvv = dvv; a.partial = partial;
     if (!k || !v || !ww || !aa || !w0 || !a0 || !k_k || !k_a || !dw || !dk2 || !dv2 || !dnkk || !dkka || !dk || !dv || !dww ||
         !daa || !partial || (a.has_vres && (!vv || !v0 || !dvfirst || !dvv)))
@@ -459,6 +507,15 @@ extern "C" int vrwkv_relu_sq_backward(size_t n, const uint16_t* x, const uint16_
 extern "C" int vrwkv_relu_sq_backward_from_act(size_t n, const uint16_t* y, const uint16_t* dy, uint16_t* dx, void* stream) {
     if (!y || !dy || !dx || (n % 8)) return vrwkv_fail(VRWKV_EINVAL, "relu_sq_backward_from_act: null pointer or n %% 8 != 0");
     relu_sq_bwd_from_act_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(y, dy, dx, n / 8);
+    VRWKV_CUDA(cudaGetLastError());
+    vrwkv_count_launch(1);
+    return VRWKV_OK;
+}
+
+extern "C" int vrwkv_reduce_partials(int nblocks, int n_times_c, const float* partial, uint16_t* out, void* stream) {
+    if (nblocks <= 0 || n_times_c <= 0 || !partial || !out) return vrwkv_fail(VRWKV_EINVAL, "reduce_partials: bad arguments");
+    if (n_times_c % 4) return vrwkv_fail(VRWKV_EINVAL, "reduce_partials: n*C must be a multiple of 4");
+    reduce_partials_kernel<<<(n_times_c / 4 + 63) / 64, 256, 0, (cudaStream_t)stream>>>(partial, out, nblocks, n_times_c);
     VRWKV_CUDA(cudaGetLastError());
     vrwkv_count_launch(1);
     return VRWKV_OK;

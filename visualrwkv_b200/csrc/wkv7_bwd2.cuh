@@ -40,40 +40,15 @@ struct alignas(128) Wkv7Bwd2Smem {
 // consecutive indices) are 16-byte chunks that are contiguous across lanes.
 __device__ __forceinline__ int perm_col(int j) { return ((j >> 2) & 1) * 32 + 4 * (j >> 3) + (j & 3); }
 
-template <int R, int NSTAGE, int UNROLL = 2>
-__global__ void __launch_bounds__((WKV_N / R) * 8 + 32)
-wkv7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_q,
-                 const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
-                 const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                 const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_sa,
-                 const Wkv7BwdArgs p) {
+// Producer + fp32 converter warp shared by the backward kernels: issues the TMA tile loads in reverse chunk order and
+// expands w into decay / decay-derivative factor and copies sa into the column-permuted fp32 tiles.
+template <int NSTAGE, class Smem>
+__device__ __forceinline__ void wkv7_bwd_producer_converter(Smem& sm, const CUtensorMap& tm_w, const CUtensorMap& tm_q,
+                                                            const CUtensorMap& tm_k, const CUtensorMap& tm_v,
+                                                            const CUtensorMap& tm_a, const CUtensorMap& tm_b,
+                                                            const CUtensorMap& tm_dy, const CUtensorMap& tm_sa, const int hh,
+                                                            const int bb, const int T, const int nchunks, const int lane) {
     constexpr int N = WKV_N, TC = WKV_TC;
-    constexpr int NCW = (N / R) * 8 / 32;
-    constexpr int TS = TC * N;
-    extern __shared__ __align__(128) uint8_t smem_bytes[];
-    Wkv7Bwd2Smem<NSTAGE>& sm = *reinterpret_cast<Wkv7Bwd2Smem<NSTAGE>*>(smem_bytes);
-
-    const int hh = blockIdx.x, bb = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const int T = p.T, H = p.H;
-    const int nchunks = T / TC;
-
-    if (tid == 0) {
-        for (int i = 0; i < NSTAGE; i++) {
-            mbar_init(&sm.full_raw[i], 1);
-            mbar_init(&sm.empty_raw[i], NCW + 1);
-        }
-        for (int i = 0; i < 2; i++) {
-            mbar_init(&sm.full_f[i], 1);
-            mbar_init(&sm.empty_f[i], NCW);
-            mbar_init(&sm.dsb_bar[i], NCW);
-        }
-        fence_mbar_init();
-    }
-    __syncthreads();
-
-    if (warp == NCW) {
         // ================= producer + fp32 converter warp =================
         auto issue = [&](int n) {  // n-th chunk in processing order = chunk nchunks-1-n
             const int stage = n % NSTAGE;
@@ -127,6 +102,43 @@ wkv7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
             }
             __syncwarp();
         }
+}
+
+template <int R, int NSTAGE, int UNROLL = 2>
+__global__ void __launch_bounds__((WKV_N / R) * 8 + 32)
+wkv7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_q,
+                 const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+                 const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                 const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_sa,
+                 const Wkv7BwdArgs p) {
+    constexpr int N = WKV_N, TC = WKV_TC;
+    constexpr int NCW = (N / R) * 8 / 32;
+    constexpr int TS = TC * N;
+    extern __shared__ __align__(128) uint8_t smem_bytes[];
+    Wkv7Bwd2Smem<NSTAGE>& sm = *reinterpret_cast<Wkv7Bwd2Smem<NSTAGE>*>(smem_bytes);
+
+    const int hh = blockIdx.x, bb = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int T = p.T, H = p.H;
+    const int nchunks = T / TC;
+
+    if (tid == 0) {
+        for (int i = 0; i < NSTAGE; i++) {
+            mbar_init(&sm.full_raw[i], 1);
+            mbar_init(&sm.empty_raw[i], NCW + 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&sm.full_f[i], 1);
+            mbar_init(&sm.empty_f[i], NCW);
+            mbar_init(&sm.dsb_bar[i], NCW);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == NCW) {
+        wkv7_bwd_producer_converter<NSTAGE>(sm, tm_w, tm_q, tm_k, tm_v, tm_a, tm_b, tm_dy, tm_sa, hh, bb, T, nchunks, lane);
         return;
     }
 

@@ -42,6 +42,15 @@ def _bf16c(*ts):
 # ------------------------------------------------------------------------------------------------------
 # thin kernel wrappers
 # ------------------------------------------------------------------------------------------------------
+def _reduce_partials(partial):
+    """[blocks, n, C] fp32 -> [n, C] bf16 in one launch (sum over blocks + cast)."""
+    L = _lib.lib()
+    nb, n, C = partial.shape
+    out = torch.empty(n, C, dtype=torch.bfloat16, device=partial.device)
+    _chk(L.vrwkv_reduce_partials(_c_int(nb), _c_int(n * C), _p(partial), _p(out), _lib.cur_stream()), "vrwkv_reduce_partials")
+    return out
+
+
 def ln_mix_forward(x2d, T, gamma, beta, eps, coefs, want_h=False):
     """x2d [rows,C] bf16 -> (list of mixed streams, h or None, stats[rows,2] f32)."""
     L = _lib.lib()
@@ -57,7 +66,7 @@ def ln_mix_forward(x2d, T, gamma, beta, eps, coefs, want_h=False):
 
 
 def ln_mix_backward(x2d, T, stats, gamma, beta, coefs, douts, dh=None, dresid=None):
-    """-> (dx, dgamma, dbeta, [dcoef...]) ; gradients of parameters in fp32."""
+    """-> (dx, dgamma, dbeta, [dcoef...]) ; parameter gradients already reduced to bf16."""
     L = _lib.lib()
     rows, C = x2d.shape
     _bf16c(x2d, gamma, beta, dh, dresid, *coefs, *douts)
@@ -67,7 +76,7 @@ def ln_mix_backward(x2d, T, stats, gamma, beta, coefs, douts, dh=None, dresid=No
     rc = L.vrwkv_ln_mix_backward(_c_int(rows), _c_int(T), _c_int(C), _c_int(len(coefs)), _p(x2d), _p(stats), _p(gamma), _p(beta),
                                  _parr(coefs), _parr(douts), _p(dh), _p(dresid), _p(dx), _p(partial), _lib.cur_stream())
     _chk(rc, "vrwkv_ln_mix_backward")
-    red = partial.sum(0)
+    red = _reduce_partials(partial)
     return dx, red[0], red[1], [red[2 + i] for i in range(len(coefs))]
 
 
@@ -82,10 +91,10 @@ def tmix_mid_forward(k, v, vfirst, ww, aa, vv, w0, a0, v0, k_k, k_a):
     return outs  # w, k2, v2, nkk, kka
 
 
-def tmix_mid_backward(k, v, vfirst, ww, aa, vv, w0, a0, v0, k_k, k_a, dw, dk2, dv2, dnkk, dkka):
+def tmix_mid_backward(k, v, vfirst, ww, aa, vv, w0, a0, v0, k_k, k_a, dw, dk2, dv2, dnkk, dkka, dk2b=None, dv2b=None):
     L = _lib.lib()
     rows, C = k.shape
-    _bf16c(k, v, vfirst, ww, aa, vv, dw, dk2, dv2, dnkk, dkka)
+    _bf16c(k, v, vfirst, ww, aa, vv, dw, dk2, dv2, dnkk, dkka, dk2b, dv2b)
     has = vfirst is not None
     dk, dv, dww, daa = [torch.empty_like(k) for _ in range(4)]
     dvf = torch.empty_like(k) if has else None
@@ -93,10 +102,10 @@ def tmix_mid_backward(k, v, vfirst, ww, aa, vv, w0, a0, v0, k_k, k_a, dw, dk2, d
     nb = L.vrwkv_tmix_blocks(_c_int(rows))
     partial = torch.empty(nb, 5, C, dtype=torch.float32, device=k.device)
     rc = L.vrwkv_tmix_mid_backward(_c_int(rows), _c_int(C), _p(k), _p(v), _p(vfirst), _p(ww), _p(aa), _p(vv), _p(w0), _p(a0),
-                                   _p(v0), _p(k_k), _p(k_a), _p(dw), _p(dk2), _p(dv2), _p(dnkk), _p(dkka), _p(dk), _p(dv),
+                                   _p(v0), _p(k_k), _p(k_a), _p(dw), _p(dk2), _p(dv2), _p(dnkk), _p(dkka), _p(dk2b), _p(dv2b), _p(dk), _p(dv),
                                    _p(dvf), _p(dww), _p(daa), _p(dvv), _p(partial), _lib.cur_stream())
     _chk(rc, "vrwkv_tmix_mid_backward")
-    red = partial.sum(0)
+    red = _reduce_partials(partial)
     return dk, dv, dvf, dww, daa, dvv, red  # red rows: dw0, da0, dv0, dk_k, dk_a
 
 
@@ -122,7 +131,7 @@ def tmix_post_backward(y, r, k2, v2, g, gamma, beta, r_k, eps, dz):
                                     _p(beta), _p(r_k), _p(dz), _p(dy), _p(dr), _p(dk2), _p(dv2), _p(dg), _p(partial),
                                     _lib.cur_stream())
     _chk(rc, "vrwkv_tmix_post_backward")
-    red = partial.sum(0)
+    red = _reduce_partials(partial)
     return dy, dr, dk2, dv2, dg, red  # red rows: dgamma, dbeta, dr_k
 
 
@@ -186,7 +195,7 @@ class LayerNormFn(torch.autograd.Function):
         x2, stats, weight, bias = ctx.saved_tensors
         dh2 = dh.reshape(x2.shape).contiguous()
         dx, dg, db, _ = ln_mix_backward(x2, x2.shape[0], stats, weight, bias, [], [], dh=dh2)
-        return dx.view(ctx.shp), dg.to(weight.dtype), db.to(bias.dtype), None
+        return dx.view(ctx.shp), dg, db, None
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -257,22 +266,20 @@ class TmixBlockFn(torch.autograd.Function):
         v4 = lambda t: t.view(B, T, H, 64)
         dw, dq, dk2b, dv2b, dnkk, dkka = wkv7_bwd_raw(v4(w), v4(r), v4(k2), v4(v2_), v4(nkk), v4(kka), v4(dy), s, sa)
         dr.add_(dq.view(rows, C))
-        dk2a.add_(dk2b.view(rows, C))
-        dv2a.add_(dv2b.view(rows, C))
         dk, dv, dvf, dww, daa, dvv, red5 = tmix_mid_backward(
             k, v, vf2, ww, aa, vv, w0.reshape(C), a0.reshape(C), v0.reshape(C) if has_vres else None, k_k.reshape(C),
-            k_a.reshape(C), dw.view(rows, C), dk2a, dv2a, dnkk.view(rows, C), dkka.view(rows, C))
+            k_a.reshape(C), dw.view(rows, C), dk2a, dv2a, dnkk.view(rows, C), dkka.view(rows, C), dk2b.view(rows, C), dv2b.view(rows, C))
         if not has_vres and dvfirst_out is not None:
             dv.add_(dvfirst_out.reshape(rows, C))
         # LoRA branches
         dhg = dg @ g2.t()
         dg2 = hg.t() @ dg
-        dpg = dhg * (hg * (1 - hg))
+        dpg = torch.ops.aten.sigmoid_backward(dhg, hg)
         dxg = dpg @ g1.t()
         dg1 = xg.t() @ dpg
         dhw = dww @ w2.t()
         dw2 = hw.t() @ dww
-        dpw = dhw * (1 - hw * hw)
+        dpw = torch.ops.aten.tanh_backward(dhw, hw)
         dxw = dpw @ w1.t()
         dw1 = xw.t() @ dpw
         dha = daa @ a2.t()
@@ -296,14 +303,13 @@ class TmixBlockFn(torch.autograd.Function):
         coefs = [c_r, c_w, c_k, c_v, c_a, c_g]
         dx, dlnw, dlnb, dco = ln_mix_backward(x2, T, stats, ln_w if with_ln else None, ln_b if with_ln else None, coefs,
                                               [dxr, dxw, dxk, dxv, dxa, dxg], dresid=do if with_ln else None)
-        pd = w0.dtype
-        sh = lambda t: t.to(pd).view(1, 1, C)
+        sh = lambda t: t.view(1, 1, C)
         grads = [dx.view(B, T, C), dvf.view(B, T, C) if has_vres else None,
-                 dlnw.to(pd) if with_ln else None, dlnb.to(pd) if with_ln else None,
+                 dlnw if with_ln else None, dlnb if with_ln else None,
                  sh(dco[0]), sh(dco[1]), sh(dco[2]), sh(dco[3]), sh(dco[4]), sh(dco[5]),
                  sh(red5[0]), dw1, dw2, sh(red5[1]), da1, da2,
                  sh(red5[2]) if has_vres else None, dv1, dv2p, dg1, dg2, sh(red5[3]), sh(red5[4]),
-                 red3[2].to(pd).view(H, 64), dWr, dWk, dWv, dWo, red3[0].to(pd), red3[1].to(pd),
+                 red3[2].view(H, 64), dWr, dWk, dWv, dWo, red3[0], red3[1],
                  None, None, None, None, None]
         return tuple(grads)
 
@@ -345,8 +351,7 @@ class CmixBlockFn(torch.autograd.Function):
         dWkey = dhk.t() @ xk
         dx, dlnw, dlnb, dco = ln_mix_backward(x2, T, stats, ln_w if with_ln else None, ln_b if with_ln else None, [ck], [dxk],
                                               dresid=do if with_ln else None)
-        pd = ck.dtype
-        return (dx.view(B, T, C), dlnw.to(pd) if with_ln else None, dlnb.to(pd) if with_ln else None, dco[0].to(pd).view(1, 1, C),
+        return (dx.view(B, T, C), dlnw if with_ln else None, dlnb if with_ln else None, dco[0].view(1, 1, C),
                 dWkey, dWval, None, None)
 
 
