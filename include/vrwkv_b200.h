@@ -67,7 +67,30 @@ int vrwkv_wkv7_forward_state(int B, int T, int H, const uint16_t* w, const uint1
                              const uint16_t* b, uint16_t* y, float* s, float* sa,
                              const float* state_in, float* state_out, void* stream);
 
-/* Kernel-variant selection for benchmarking (0 = default heuristic). Thread-safe, process-wide. */
+/* Extended entry points: `flags` may carry VRWKV_WKV7_BOUNDED_DECAY, the caller's promise that exp(w) <= 0.607
+ * everywhere — true for RWKV-7's w = -softplus(.) - 0.5 (VisualRWKV-v7/v7.00/src/model.py:176), i.e. for every call
+ * RWKV_Tmix_x070 makes (model.py:190).  With it (and T % 64 == 0) the library evaluates the recurrence 64 steps at a
+ * time on the tensor cores: forward = chunked kernel, backward = tensor-core scan of dL/dS at chunk boundaries + the
+ * step-by-step kernel on all 64-step segments concurrently.  Without it (the plain entry points above, which is what
+ * torch.ops.wind_backstepping binds) the step-by-step kernels run for any w.  Same tensors, same contract. */
+#define VRWKV_WKV7_BOUNDED_DECAY 1u
+int vrwkv_wkv7_forward_ex(int B, int T, int H, const uint16_t* w, const uint16_t* q,
+                          const uint16_t* k, const uint16_t* v, const uint16_t* a,
+                          const uint16_t* b, uint16_t* y, float* s, float* sa,
+                          const float* state_in, float* state_out, unsigned flags, void* stream);
+int vrwkv_wkv7_backward_ex(int B, int T, int H, const uint16_t* w, const uint16_t* q,
+                           const uint16_t* k, const uint16_t* v, const uint16_t* a,
+                           const uint16_t* b, const uint16_t* dy, const float* s, const float* sa,
+                           uint16_t* dw, uint16_t* dq, uint16_t* dk, uint16_t* dv, uint16_t* da,
+                           uint16_t* db, unsigned flags, void* stream);
+/* Synchronises the device and fails (VRWKV_EINVAL) if a chunked kernel saw decay outside the promised range since
+ * the last check; the flag is cleared. */
+int vrwkv_wkv7_domain_check(void);
+/* Development aid: per-phase clock stamps of the chunked forward kernel are written to buf (NULL disables). */
+int vrwkv_wkv7_chunk_debug(float* buf);
+
+/* Kernel-variant selection for benchmarking (0 = default heuristic; forward 1/2 step-by-step, 3 chunked;
+ * backward 1/2 step-by-step, 3 segmented). Thread-safe, process-wide. */
 int vrwkv_wkv7_set_variant(int fwd_variant, int bwd_variant);
 
 

@@ -128,3 +128,25 @@ def test_oracle_reproduces_reference_kernel_goldens(path):
 
 def test_goldens_present():
     assert len(GOLDEN) >= 2
+
+
+@pytest.mark.parametrize("L", [16, 64])
+def test_chunked_restatement_equals_step_by_step_oracle(L):
+    """oracle/wkv7_chunked.py (the algebra of the tensor-core kernels) against the step-by-step fp64 oracle."""
+    import torch
+    from oracle import wkv7_chunked as C
+    cpu = O.make_inputs(2, 128, 2, 64, seed=13)
+    y64, s64, sa64 = O.forward(*cpu[:6])
+    g64 = O.backward_exact(*cpu)
+    y, sa, s_start, s_end = C.chunk_forward(*cpu[:6], L=L, dtype=torch.float64)
+    assert O.err_ratio(y.numpy(), y64) < 1e-12 and O.err_ratio(sa.numpy(), sa64) < 1e-12
+    # state at the start of chunk c = transposed checkpoint after step c*L - 1
+    for c in range(1, 128 // L):
+        ck = s64[:, :, c * L // 16 - 1].transpose(0, 1, 3, 2)
+        assert O.err_ratio(s_start[:, :, c].numpy(), ck) < 1e-12
+    g = C.chunk_backward(*cpu, L=L, dtype=torch.float64)
+    for x, r in zip(g, g64):
+        assert O.err_ratio(x.numpy(), np.asarray(r)) < 1e-11
+    # TF32 operand rounding (what the kernels do) stays well inside the output rounding of bf16
+    yt, sat, _, _ = C.chunk_forward(*cpu[:6], L=64, dtype=torch.float32, rnd=C.tf32_round)
+    assert O.err_ratio(yt.numpy(), y64) < 8e-4 and O.err_ratio(sat.numpy(), sa64) < 8e-4

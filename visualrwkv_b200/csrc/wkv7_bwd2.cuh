@@ -47,14 +47,15 @@ __device__ __forceinline__ void wkv7_bwd_producer_converter(Smem& sm, const CUte
                                                             const CUtensorMap& tm_k, const CUtensorMap& tm_v,
                                                             const CUtensorMap& tm_a, const CUtensorMap& tm_b,
                                                             const CUtensorMap& tm_dy, const CUtensorMap& tm_sa, const int hh,
-                                                            const int bb, const int T, const int nchunks, const int lane) {
+                                                            const int bb, const int T, const int c_top, const int nchunks, const int lane) {
+    // processes chunks c_top-1, c_top-2, ... (nchunks of them)
     constexpr int N = WKV_N, TC = WKV_TC;
         // ================= producer + fp32 converter warp =================
-        auto issue = [&](int n) {  // n-th chunk in processing order = chunk nchunks-1-n
+        auto issue = [&](int n) {  // n-th chunk in processing order = chunk c_top-1-n
             const int stage = n % NSTAGE;
             uint64_t* bar = &sm.full_raw[stage];
             mbar_arrive_expect_tx(bar, 7 * TC * N * 2 + TC * N * 4);
-            const int x0 = hh * N, y0 = bb * T + (nchunks - 1 - n) * TC;
+            const int x0 = hh * N, y0 = bb * T + (c_top - 1 - n) * TC;
             tma_load_2d(&sm.raw[stage][0][0][0], &tm_w, x0, y0, bar);
             tma_load_2d(&sm.raw[stage][1][0][0], &tm_q, x0, y0, bar);
             tma_load_2d(&sm.raw[stage][2][0][0], &tm_k, x0, y0, bar);
@@ -121,7 +122,11 @@ wkv7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int T = p.T, H = p.H;
-    const int nchunks = T / TC;
+    const int nchunks_all = T / TC;
+    const int span = p.span > 0 ? p.span : nchunks_all;
+    const int seg = blockIdx.z;
+    const int c_lo = seg * span, c_top = min(nchunks_all, c_lo + span);
+    const int nchunks = c_top - c_lo;  // 16-step chunks this CTA walks (from c_top-1 down to c_lo)
 
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; i++) {
@@ -138,7 +143,7 @@ wkv7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     __syncthreads();
 
     if (warp == NCW) {
-        wkv7_bwd_producer_converter<NSTAGE>(sm, tm_w, tm_q, tm_k, tm_v, tm_a, tm_b, tm_dy, tm_sa, hh, bb, T, nchunks, lane);
+        wkv7_bwd_producer_converter<NSTAGE>(sm, tm_w, tm_q, tm_k, tm_v, tm_a, tm_b, tm_dy, tm_sa, hh, bb, T, c_top, nchunks, lane);
         return;
     }
 
@@ -157,7 +162,7 @@ wkv7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         for (int c = 0; c < 4; c++) ST[r][c] = dS[r][c] = dST[r][c] = 0ull;
 
     // checkpoint memory [row = i][col = j] holds S_{j,i} (stored transposed by the forward, wkv7_cuda.cu:44-50)
-    const float* sbase = p.s + ((size_t)bb * H + hh) * nchunks * N * N + (size_t)i0 * N + 8 * l;
+    const float* sbase = p.s + ((size_t)bb * H + hh) * nchunks_all * N * N + (size_t)i0 * N + 8 * l;
     float4 pf[R][2];
     auto prefetch = [&](int c) {
 #pragma unroll
@@ -166,7 +171,19 @@ wkv7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
             pf[r][1] = __ldg(reinterpret_cast<const float4*>(sbase + (size_t)c * N * N + r * N + 4));
         }
     };
-    prefetch(nchunks - 1);
+    prefetch(c_top - 1);
+    if (p.ds_in && c_top < nchunks_all) {
+        // dL/dS at the end of this segment, in both orientations (dS_ij and dS_ji)
+        const float* src = p.ds_in + (((size_t)bb * H + hh) * gridDim.z + seg) * N * N;
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int c2 = 0; c2 < 4; c2++) {
+                const int j = 8 * l + 2 * c2;
+                dS[r][c2] = pk2(__ldg(src + (i0 + r) * N + j), __ldg(src + (i0 + r) * N + j + 1));
+                dST[r][c2] = pk2(__ldg(src + (size_t)j * N + i0 + r), __ldg(src + (size_t)(j + 1) * N + i0 + r));
+            }
+    }
 
     // which gradient rows this lane stores (see header): E after phase B1, F (R==4 only) with it, G after phase B2
     uint16_t *pE, *pF = nullptr, *pG;
@@ -321,13 +338,13 @@ wkv7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     };
 
     for (int n = 0; n < nchunks; n++) {
-        const int c = nchunks - 1 - n, buf = n & 1, stage = n % NSTAGE;
+        const int c = c_top - 1 - n, buf = n & 1, stage = n % NSTAGE;
 #pragma unroll
         for (int r = 0; r < R; r++) {
             ST[r][0] = pk2(pf[r][0].x, pf[r][0].y); ST[r][1] = pk2(pf[r][0].z, pf[r][0].w);
             ST[r][2] = pk2(pf[r][1].x, pf[r][1].y); ST[r][3] = pk2(pf[r][1].z, pf[r][1].w);
         }
-        if (c > 0) prefetch(c - 1);
+        if (c > c_lo) prefetch(c - 1);
         mbar_wait(&sm.full_raw[stage], (n / NSTAGE) & 1);
         mbar_wait(&sm.full_f[buf], (n >> 1) & 1);
         __syncwarp();

@@ -1,0 +1,502 @@
+// wkv7_chunk_fwd.cuh — WKV7 forward evaluated chunk by chunk on the tcgen05 tensor cores (TF32 operands, fp32 TMEM
+// accumulators).  Same operator contract as the step-by-step kernels (wkv7_fwd2.cuh) and the reference forward_kernel
+// (VisualRWKV-v7/v7.00/cuda/wkv7_cuda.cu:10-52): y (bf16), sa (fp32, every step), s (fp32, transposed state every 16
+// steps); the chunk-wise restatement kept with the tests states the algebra and is checked against the step-by-step oracle.
+//
+// One 512-thread CTA per (batch, head) walks the sequence in chunks of L = 64 steps.  With G_t the running sum of
+// -exp(w) inside the chunk and  At = a exp(G_{t-1}), Qt = q exp(G_t), Kt = k exp(-G_t), Bt = b exp(-G_t):
+//   scores  = [At;Qt] [Bt;Kt]^T      (128x128x64)  -> A_ab, A_ak (strictly lower), A_qb, A_qk (lower triangular)
+//   ACC     = [A_ak;A_qk] V          (128x64x64)   rows 0-63: AV
+//   Tinv    = (I - A_ab)^-1          fp32 on the CUDA cores: two 32x32 triangular inverses + the coupling block
+//   TX      = Tinv [At | AV]         (64x128x64)   = [Ah | Uh]
+//   CORR    = [A_ab;A_qb] Ah ;  ACC += [A_ab;A_qb] Uh          => [At;Qt] + CORR = [Ah;Qp],  ACC = [Uh; Y_intra]
+//   ACC    += [Ah;Qp] S_0^T                                    => ACC = [U; Y]  (rows of U are the sa_t)
+//   STATE  += U^T Bt + V^T Kt  in four 16-step groups (checkpoint after each), then S_L = STATE diag(exp(G_L))
+// Operand layouts: K-major operands use SWIZZLE_128B rows of 32 tf32; [Bt;Kt], [U;V] and [At|AV] -> [Ah|Uh] are
+// stored row-major [step][channel] in the SWIZZLE_128B_BASE32B layout and consumed MN-major, so nothing is transposed
+// by hand.  Every MMA is issued by thread 0 and followed by a commit that all threads wait for (the phases are
+// sequential; the tensor-core time per chunk is ~1.5k cycles, the rest is operand preparation on the CUDA cores).
+// Domain: exp(+-G) must stay finite, i.e. sum over a chunk of exp(w) < ~85 — guaranteed by RWKV-7's
+// w = -softplus(.) - 0.5 (exp(w) <= 0.607, model.py:176); the host dispatcher keeps the step-by-step kernel for
+// callers that cannot promise that.
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+#include "wkv7_fwd.cuh"
+
+namespace vrwkv {
+
+constexpr int CK_L = 64;        // steps per chunk
+constexpr int CK_THREADS = 512;
+
+__device__ int g_chunk_domain_err = 0;    // set when a chunk's accumulated decay leaves the fp32-safe range
+__device__ float* g_chunk_dbg = nullptr;  // development aid: when set, CTA (0,0) records per-phase clocks of chunk 1
+
+struct alignas(1024) Wkv7ChunkSmem {
+    uint8_t in[6 * CK_L * WKV_N * 2];  // TMA tiles w,q,k,v,a,b [64][64] bf16; later RMN (32 KB) and TINV (16 KB)
+    uint8_t aq[32768];                 // A operand [At;Qt] -> [Ah;Qp]: 2 k-atoms x 128 rows x 128 B (also TINV's tail)
+    uint8_t bk[32768];                 // B operand [Bt;Kt] of the score product (K-major); then `sc`
+    uint8_t bk2[32768];                // [Bt;Kt], MN-major (rows = step: Bt 0-63, Kt 64-127; 2 channel blocks)
+    uint8_t uv[32768];                 // [U;V], MN-major (rows = step: U 0-63, V 64-127; 2 channel blocks)
+    uint8_t sb[16384];                 // B operand S_0 [i][j] (tf32): 2 k-atoms x 64 rows
+    uint8_t aab[16384];                // A_ab fp32 [t][s], 16-byte chunks XOR-swizzled by (t & 7)
+    float esc[32 * 32];                // coupling-block scratch of the inverse
+    float part[8][WKV_N];              // per row-group decay sums
+    float echk[4][WKV_N];              // exp(G_t) at t = 15, 31, 47, 63
+    uint64_t bar_in, bar_mma;
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(CK_THREADS, 1)
+wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_q,
+                      const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+                      const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                      const Wkv7FwdArgs p) {
+    constexpr int N = WKV_N, L = CK_L;
+    extern __shared__ __align__(1024) uint8_t chunk_smem_bytes[];
+    Wkv7ChunkSmem& sm = *reinterpret_cast<Wkv7ChunkSmem*>(chunk_smem_bytes);
+    uint8_t* const rmn = sm.in;           // [At|AV] -> [Ah|Uh], MN-major: 4 channel blocks x 64 k-lines x 128 B
+    uint8_t* const tinv = sm.in + 32768;  // A operand Tinv (K-major): 2 k-atoms x 64 rows (rows 64-127 alias what follows)
+    uint8_t* const sc = sm.bk;            // A operand [A_ak;A_qk], then [A_ab;A_qb]
+
+    const int hh = blockIdx.x, bb = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int qd = warp & 3, cs = warp >> 2;  // TMEM lane quadrant / column slice of this warp
+    const int r = 32 * qd + lane;             // accumulator row (TMEM lane) of this thread
+    const int t_r = r & 63;
+    const int T = p.T, H = p.H;
+    const int nch = T / L;
+
+    if (tid == 0) {
+        mbar_init(&sm.bar_in, 1);
+        mbar_init(&sm.bar_mma, 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k);
+        tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b);
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc<512>(&sm.tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+    const uint32_t tm_row = tmem + ((uint32_t)(32 * qd) << 16);
+    constexpr uint32_t C_SC = 0, C_UY = 128, C_CORR = 192, C_ST = 256, C_TX = 320;
+
+    auto issue_loads = [&](int c) {
+        mbar_arrive_expect_tx(&sm.bar_in, 6 * L * N * 2);
+        const int x0 = hh * N, y0 = bb * T + c * L;
+        tma_load_2d(sm.in + 0 * 8192, &tm_w, x0, y0, &sm.bar_in);
+        tma_load_2d(sm.in + 1 * 8192, &tm_q, x0, y0, &sm.bar_in);
+        tma_load_2d(sm.in + 2 * 8192, &tm_k, x0, y0, &sm.bar_in);
+        tma_load_2d(sm.in + 3 * 8192, &tm_v, x0, y0, &sm.bar_in);
+        tma_load_2d(sm.in + 4 * 8192, &tm_a, x0, y0, &sm.bar_in);
+        tma_load_2d(sm.in + 5 * 8192, &tm_b, x0, y0, &sm.bar_in);
+    };
+    if (tid == 0) issue_loads(0);
+    __syncwarp();
+    float* const dbg = (hh == 0 && bb == 0) ? g_chunk_dbg : nullptr;
+
+    // ---- initial state: STATE accumulator (fp32) and its tf32 image as the B operand of the first chunk ----
+    if (r < N) {  // row i = r, columns 16cs .. 16cs+15
+        uint32_t v[16];
+        if (p.state_in) {
+            const float4* src = reinterpret_cast<const float4*>(p.state_in + (((size_t)bb * H + hh) * N + r) * N + 16 * cs);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; c4++) {
+                const float4 x = __ldg(src + c4);
+                v[4 * c4] = __float_as_uint(x.x); v[4 * c4 + 1] = __float_as_uint(x.y);
+                v[4 * c4 + 2] = __float_as_uint(x.z); v[4 * c4 + 3] = __float_as_uint(x.w);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 16; e++) v[e] = 0u;
+        }
+        tmem_st16(tm_row + C_ST + 16 * cs, v);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; c4++) {
+            const int ch = 4 * (cs & 1) + c4;
+            *reinterpret_cast<float4*>(sm.sb + (cs >> 1) * 8192 + r * 128 + ((ch ^ (r & 7)) << 4)) =
+                rt32(make_float4(__uint_as_float(v[4 * c4]), __uint_as_float(v[4 * c4 + 1]), __uint_as_float(v[4 * c4 + 2]),
+                                 __uint_as_float(v[4 * c4 + 3])));
+        }
+        tmem_st_wait();
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    long long tstamp0 = 0;
+    int tsi = 0;
+    auto stamp = [&](int c) {
+        if (dbg && c == 1 && tid == 0) {
+            const long long now = clock64();
+            if (tsi == 0) tstamp0 = now;
+            dbg[2048 + tsi++] = (float)(now - tstamp0);
+        }
+    };
+    uint32_t mph = 0;  // phase of bar_mma (every commit is waited for before the next one is issued)
+    auto mma_wait = [&](int c) {
+        stamp(c);
+        mbar_wait(&sm.bar_mma, mph & 1);
+        mph++;
+        tc_fence_after();
+        __syncwarp();
+        stamp(c);
+    };
+    auto operands_ready = [&]() {  // generic-proxy writes -> visible to the tensor core, then CTA barrier
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+    };
+    constexpr uint32_t ID_128x128 = umma_idesc_tf32(128, 128), ID_128x64 = umma_idesc_tf32(128, 64),
+                       ID_B_MN_64 = umma_idesc_tf32(128, 64, 0, 1), ID_B_MN_128 = umma_idesc_tf32(128, 128, 0, 1),
+                       ID_ST = umma_idesc_tf32(128, 64, 1, 1);
+
+    for (int c = 0; c < nch; c++) {
+        stamp(c);
+        mbar_wait(&sm.bar_in, c & 1);
+        stamp(c);
+        // ================= P1: decay prefix sums and scaled operands (8 rows x 1 column per thread) =================
+        {
+            const int hf = warp & 1, rg = warp >> 1;
+            const int j = 32 * hf + lane;
+            const uint16_t* in16 = reinterpret_cast<const uint16_t*>(sm.in);
+            float g[8];
+            float loc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                g[k] = -__expf(bf16lo_to_f32(in16[0 * 4096 + (8 * rg + k) * N + j]));
+                loc += g[k];
+            }
+            sm.part[rg][j] = loc;
+            __syncthreads();
+            float G = 0.f;
+#pragma unroll
+            for (int k = 0; k < 7; k++) G += (k < rg) ? sm.part[k][j] : 0.f;
+            float Eprev = __expf(G);
+            uint8_t* const aq_a = sm.aq + hf * 16384;
+            uint8_t* const bk_a = sm.bk + hf * 16384;
+            uint8_t* const uv_a = sm.uv + hf * 16384;
+            uint8_t* const bk2_a = sm.bk2 + hf * 16384;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int t = 8 * rg + k;
+                G += g[k];
+                const float E = __expf(G), F = __expf(-G);
+                const float qv = bf16lo_to_f32(in16[1 * 4096 + t * N + j]), kv = bf16lo_to_f32(in16[2 * 4096 + t * N + j]);
+                const float vv = bf16lo_to_f32(in16[3 * 4096 + t * N + j]), av_ = bf16lo_to_f32(in16[4 * 4096 + t * N + j]);
+                const float bv = bf16lo_to_f32(in16[5 * 4096 + t * N + j]);
+                const float bt = rt32(bv * F), kt = rt32(kv * F);
+                *reinterpret_cast<float*>(aq_a + sw128_off(t, lane)) = rt32(av_ * Eprev);
+                *reinterpret_cast<float*>(aq_a + sw128_off(64 + t, lane)) = rt32(qv * E);
+                *reinterpret_cast<float*>(bk_a + sw128_off(t, lane)) = bt;
+                *reinterpret_cast<float*>(bk_a + sw128_off(64 + t, lane)) = kt;
+                *reinterpret_cast<float*>(bk2_a + sw32_off(t, lane)) = bt;
+                *reinterpret_cast<float*>(bk2_a + sw32_off(64 + t, lane)) = kt;
+                *reinterpret_cast<float*>(uv_a + sw32_off(64 + t, lane)) = vv;  // bf16 values are exact in tf32
+                if ((t & 15) == 15) sm.echk[t >> 4][j] = E;
+                if (t == L - 1 && G < -80.f) g_chunk_domain_err = 1;
+                Eprev = E;
+            }
+        }
+        operands_ready();
+        // ================= scores =================
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint64_t da = umma_desc_advance(umma_desc_sw128(sm.aq + (k >> 2) * 16384), (k & 3) * 32);
+                const uint64_t db = umma_desc_advance(umma_desc_sw128(sm.bk + (k >> 2) * 16384), (k & 3) * 32);
+                umma_tf32(tmem + C_SC, da, db, ID_128x128, k > 0);
+            }
+            umma_commit(&sm.bar_mma);
+        }
+        mma_wait(c);
+        // ================= P2: masks; [A_ak;A_qk] operand; A_ab in fp32 for the inverse =================
+        float sc0[32];  // warps with cs < 2 keep their slice of [A_ab;A_qb] until the operand buffer is free again
+        {
+            uint32_t v[32];
+            const bool incl = r >= 64;  // q rows keep the diagonal
+            tmem_ld32(tm_row + C_SC + 32 * cs, v);
+            const int sbase = 32 * (cs & 1);
+#pragma unroll
+            for (int e = 0; e < 32; e++) {
+                const int s = sbase + e;
+                const bool keep = incl ? (s <= t_r) : (s < t_r);
+                sc0[e] = keep ? __uint_as_float(v[e]) : 0.f;
+            }
+            if (cs < 2) {
+                if (r < 64) {
+#pragma unroll
+                    for (int cc = 0; cc < 8; cc++)
+                        *reinterpret_cast<float4*>(sm.aab + r * 256 + (((8 * cs + cc) ^ (r & 7)) << 4)) =
+                            make_float4(sc0[4 * cc], sc0[4 * cc + 1], sc0[4 * cc + 2], sc0[4 * cc + 3]);
+                }
+            } else {
+#pragma unroll
+                for (int cc = 0; cc < 8; cc++)
+                    *reinterpret_cast<float4*>(sc + (cs & 1) * 16384 + r * 128 + ((cc ^ (r & 7)) << 4)) =
+                        rt32(make_float4(sc0[4 * cc], sc0[4 * cc + 1], sc0[4 * cc + 2], sc0[4 * cc + 3]));
+            }
+        }
+        operands_ready();
+        // ================= ACC = [A_ak;A_qk] V (runs while the inverse is being computed) =================
+        if (tid == 0) {
+            tc_fence_after();
+            const uint64_t dbv = umma_desc_mn_tf32(sm.uv + 64 * 128, 16384, 512);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint64_t da = umma_desc_advance(umma_desc_sw128(sc + (k >> 2) * 16384), (k & 3) * 32);
+                umma_tf32(tmem + C_UY, da, umma_desc_advance(dbv, k * 1024), ID_B_MN_64, k > 0);
+            }
+            umma_commit(&sm.bar_mma);
+        }
+        // ================= I1: inverses of the two 32x32 diagonal blocks of T = I - A_ab (one column per thread) ====
+        if (warp < 2) {
+            const int bl = warp, cc = lane;
+            float x[32];
+#pragma unroll
+            for (int t = 0; t < 32; t++) {
+                float a0 = (t == cc) ? 1.f : 0.f, a1 = 0.f;
+#pragma unroll
+                for (int c4 = 0; c4 < (t + 3) / 4; c4++) {
+                    const float4 m = *reinterpret_cast<const float4*>(sm.aab + (32 * bl + t) * 256 + (((8 * bl + c4) ^ (t & 7)) << 4));
+                    const float mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int s = 4 * c4 + e;
+                        if (s < t) {
+                            if (s & 1) a1 = fmaf(mm[e], x[s], a1);
+                            else a0 = fmaf(mm[e], x[s], a0);
+                        }
+                    }
+                }
+                x[t] = a0 + a1;
+                *reinterpret_cast<float*>(tinv + bl * 8192 + sw128_off(32 * bl + t, cc)) = rt32(x[t]);
+            }
+        } else if (warp < 10) {
+            // zero the upper-right block of Tinv (rows 0-31, k 32-63): 32 rows x 128 B
+            const int z = tid - 64;  // 0..255
+            *reinterpret_cast<float4*>(tinv + 8192 + z * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (warp < 14) {
+            // At (K-major rows 0-63 of aq) -> rmn blocks 0,1 (MN-major, k-line = step)
+            const int z = tid - 320;            // 0..127
+            const int t = z >> 1, half = z & 1;  // 8 chunks of 16 B each
+#pragma unroll
+            for (int cc = 0; cc < 8; cc++) {
+                const int ch = 8 * half + cc;  // 16-byte chunk 0..15 of the 64-float row
+                const float4 val = *reinterpret_cast<const float4*>(sm.aq + (ch >> 3) * 16384 + t * 128 + (((ch & 7) ^ (t & 7)) << 4));
+                *reinterpret_cast<float4*>(rmn + (ch >> 3) * 8192 + sw32_off(t, 4 * (ch & 7))) = val;
+            }
+        }
+        mma_wait(c);
+        // ================= P3: AV -> rmn blocks 2,3; [A_ab;A_qb] operand =================
+        if (r < 64) {
+            uint32_t v[16];
+            tmem_ld16(tm_row + C_UY + 16 * cs, v);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; c4++)
+                *reinterpret_cast<float4*>(rmn + (2 + (cs >> 1)) * 8192 + sw32_off(r, 16 * (cs & 1) + 4 * c4)) =
+                    rt32(make_float4(__uint_as_float(v[4 * c4]), __uint_as_float(v[4 * c4 + 1]), __uint_as_float(v[4 * c4 + 2]),
+                                     __uint_as_float(v[4 * c4 + 3])));
+        }
+        if (cs < 2) {
+#pragma unroll
+            for (int cc = 0; cc < 8; cc++)
+                *reinterpret_cast<float4*>(sc + cs * 16384 + r * 128 + ((cc ^ (r & 7)) << 4)) =
+                    rt32(make_float4(sc0[4 * cc], sc0[4 * cc + 1], sc0[4 * cc + 2], sc0[4 * cc + 3]));
+        }
+        __syncthreads();
+        // ================= I2: E = A_c X_a  (A_c = A_ab[32+t][s], X_a = Tinv rows/cols 0-31) =================
+        {
+            const int t = tid >> 4, c0 = 2 * (tid & 15);
+            float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+            for (int c4 = 0; c4 < 8; c4++) {
+                const float4 m = *reinterpret_cast<const float4*>(sm.aab + (32 + t) * 256 + ((c4 ^ (t & 7)) << 4));
+                const float mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int s = 4 * c4 + e;
+                    const float2 xa = *reinterpret_cast<const float2*>(tinv + sw128_off(s, c0));
+                    e0 = fmaf(mm[e], xa.x, e0);
+                    e1 = fmaf(mm[e], xa.y, e1);
+                }
+            }
+            *reinterpret_cast<float2*>(&sm.esc[t * 32 + c0]) = make_float2(e0, e1);
+        }
+        __syncthreads();
+        // ================= I3: X_c = X_b E  -> Tinv rows 32-63, k 0-31 =================
+        {
+            const int t = tid >> 4, c0 = 2 * (tid & 15);
+            float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+            for (int c4 = 0; c4 < 8; c4++) {
+                const float4 m = *reinterpret_cast<const float4*>(tinv + 8192 + (32 + t) * 128 + ((c4 ^ (t & 7)) << 4));
+                const float mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const float2 ev = *reinterpret_cast<const float2*>(&sm.esc[(4 * c4 + e) * 32 + c0]);
+                    e0 = fmaf(mm[e], ev.x, e0);
+                    e1 = fmaf(mm[e], ev.y, e1);
+                }
+            }
+            *reinterpret_cast<float2*>(tinv + sw128_off(32 + t, c0)) = make_float2(rt32(e0), rt32(e1));
+        }
+        operands_ready();
+        // ================= TX = Tinv [At | AV] =================
+        if (tid == 0) {
+            tc_fence_after();
+            const uint64_t dbr = umma_desc_mn_tf32(rmn, 8192, 512);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint64_t da = umma_desc_advance(umma_desc_sw128(tinv + (k >> 2) * 8192), (k & 3) * 32);
+                umma_tf32(tmem + C_TX, da, umma_desc_advance(dbr, k * 1024), ID_B_MN_128, k > 0);
+            }
+            umma_commit(&sm.bar_mma);
+        }
+        mma_wait(c);
+        // ================= [Ah | Uh] -> rmn (row-major, read MN-major by the next products) =================
+        if (r < 64) {
+            uint32_t v[32];
+            tmem_ld32(tm_row + C_TX + 32 * cs, v);
+#pragma unroll
+            for (int cc = 0; cc < 8; cc++)
+                *reinterpret_cast<float4*>(rmn + cs * 8192 + sw32_off(r, 4 * cc)) =
+                    rt32(make_float4(__uint_as_float(v[4 * cc]), __uint_as_float(v[4 * cc + 1]), __uint_as_float(v[4 * cc + 2]),
+                                     __uint_as_float(v[4 * cc + 3])));
+        }
+        operands_ready();
+        // ================= CORR = [A_ab;A_qb] Ah ;  ACC += [A_ab;A_qb] Uh =================
+        if (tid == 0) {
+            tc_fence_after();
+            const uint64_t dbh = umma_desc_mn_tf32(rmn, 8192, 512), dbu = umma_desc_mn_tf32(rmn + 2 * 8192, 8192, 512);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint64_t da = umma_desc_advance(umma_desc_sw128(sc + (k >> 2) * 16384), (k & 3) * 32);
+                umma_tf32(tmem + C_CORR, da, umma_desc_advance(dbh, k * 1024), ID_B_MN_64, k > 0);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint64_t da = umma_desc_advance(umma_desc_sw128(sc + (k >> 2) * 16384), (k & 3) * 32);
+                umma_tf32(tmem + C_UY, da, umma_desc_advance(dbu, k * 1024), ID_B_MN_64, 1);
+            }
+            umma_commit(&sm.bar_mma);
+        }
+        mma_wait(c);
+        if (tid == 0 && c + 1 < nch) issue_loads(c + 1);  // rmn / tinv are dead: the input buffer is free again
+        __syncwarp();
+        // ================= P5: [At;Qt] += CORR  ->  [Ah;Qp] =================
+        {
+            uint32_t v[16];
+            tmem_ld16(tm_row + C_CORR + 16 * cs, v);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; c4++) {
+                const int ch = 4 * (cs & 1) + c4;
+                float4* ptr = reinterpret_cast<float4*>(sm.aq + (cs >> 1) * 16384 + r * 128 + ((ch ^ (r & 7)) << 4));
+                float4 o = *ptr;
+                o.x = rt32(o.x + __uint_as_float(v[4 * c4]));
+                o.y = rt32(o.y + __uint_as_float(v[4 * c4 + 1]));
+                o.z = rt32(o.z + __uint_as_float(v[4 * c4 + 2]));
+                o.w = rt32(o.w + __uint_as_float(v[4 * c4 + 3]));
+                *ptr = o;
+            }
+        }
+        operands_ready();
+        // ================= ACC += [Ah;Qp] S_0^T  ->  [U;Y] =================
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint64_t da = umma_desc_advance(umma_desc_sw128(sm.aq + (k >> 2) * 16384), (k & 3) * 32);
+                const uint64_t db = umma_desc_advance(umma_desc_sw128(sm.sb + (k >> 2) * 8192), (k & 3) * 32);
+                umma_tf32(tmem + C_UY, da, db, ID_128x64, 1);
+            }
+            umma_commit(&sm.bar_mma);
+        }
+        mma_wait(c);
+        // ================= P6: sa and y to global memory; U operand =================
+        {
+            uint32_t v[16];
+            tmem_ld16(tm_row + C_UY + 16 * cs, v);
+            const size_t row = (((size_t)bb * T + (size_t)c * L + t_r) * H + hh) * N + 16 * cs;
+            if (r < 64) {
+#pragma unroll
+                for (int c4 = 0; c4 < 4; c4++) {
+                    const float4 u = make_float4(__uint_as_float(v[4 * c4]), __uint_as_float(v[4 * c4 + 1]),
+                                                 __uint_as_float(v[4 * c4 + 2]), __uint_as_float(v[4 * c4 + 3]));
+                    if (p.sa) *reinterpret_cast<float4*>(p.sa + row + 4 * c4) = u;
+                    *reinterpret_cast<float4*>(sm.uv + (cs >> 1) * 16384 + sw32_off(r, 16 * (cs & 1) + 4 * c4)) = rt32(u);
+                }
+            } else {
+                uint4 o0, o1;
+                o0.x = pack_bf16x2(__uint_as_float(v[0]), __uint_as_float(v[1]));
+                o0.y = pack_bf16x2(__uint_as_float(v[2]), __uint_as_float(v[3]));
+                o0.z = pack_bf16x2(__uint_as_float(v[4]), __uint_as_float(v[5]));
+                o0.w = pack_bf16x2(__uint_as_float(v[6]), __uint_as_float(v[7]));
+                o1.x = pack_bf16x2(__uint_as_float(v[8]), __uint_as_float(v[9]));
+                o1.y = pack_bf16x2(__uint_as_float(v[10]), __uint_as_float(v[11]));
+                o1.z = pack_bf16x2(__uint_as_float(v[12]), __uint_as_float(v[13]));
+                o1.w = pack_bf16x2(__uint_as_float(v[14]), __uint_as_float(v[15]));
+                *reinterpret_cast<uint4*>(p.y + row) = o0;
+                *reinterpret_cast<uint4*>(p.y + row + 8) = o1;
+            }
+        }
+        operands_ready();
+        // ================= STATE += U^T Bt + V^T Kt, 16 steps at a time =================
+#pragma unroll 1
+        for (int g = 0; g < 4; g++) {
+            if (tid == 0) {
+                tc_fence_after();
+                const uint64_t da = umma_desc_mn_tf32(sm.uv, 16384, 512);
+                const uint64_t db = umma_desc_mn_tf32(sm.bk2, 16384, 512);
+#pragma unroll
+                for (int part = 0; part < 2; part++)
+#pragma unroll
+                    for (int x = 0; x < 2; x++) {
+                        const uint32_t off = (uint32_t)(part * 64 + 16 * g + 8 * x) * 128;
+                        umma_tf32(tmem + C_ST, umma_desc_advance(da, off), umma_desc_advance(db, off), ID_ST, 1);
+                    }
+                umma_commit(&sm.bar_mma);
+            }
+            mma_wait(c);
+            if (r < 64) {  // row i = r, columns j = 16cs .. 16cs+15
+                uint32_t v[16];
+                tmem_ld16(tm_row + C_ST + 16 * cs, v);
+                float* ck = p.s ? p.s + ((((size_t)bb * H + hh) * (T / WKV_TC) + (size_t)c * 4 + g) * N + 16 * cs) * N + r : nullptr;
+                float sv[16];
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    sv[e] = __uint_as_float(v[e]) * sm.echk[g][16 * cs + e];
+                    if (ck) ck[(size_t)e * N] = sv[e];  // transposed checkpoint [j][i] (wkv7_cuda.cu:44-50)
+                }
+                if (g == 3) {
+#pragma unroll
+                    for (int e = 0; e < 16; e++) v[e] = __float_as_uint(sv[e]);
+                    tmem_st16(tm_row + C_ST + 16 * cs, v);
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; c4++) {
+                        const int ch = 4 * (cs & 1) + c4;
+                        *reinterpret_cast<float4*>(sm.sb + (cs >> 1) * 8192 + r * 128 + ((ch ^ (r & 7)) << 4)) =
+                            rt32(make_float4(sv[4 * c4], sv[4 * c4 + 1], sv[4 * c4 + 2], sv[4 * c4 + 3]));
+                    }
+                    if (p.state_out && c == nch - 1) {
+                        float4* dst = reinterpret_cast<float4*>(p.state_out + (((size_t)bb * H + hh) * N + r) * N + 16 * cs);
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; c4++) dst[c4] = make_float4(sv[4 * c4], sv[4 * c4 + 1], sv[4 * c4 + 2], sv[4 * c4 + 3]);
+                    }
+                    tmem_st_wait();
+                }
+            }
+            operands_ready();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace vrwkv

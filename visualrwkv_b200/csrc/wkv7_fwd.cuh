@@ -20,6 +20,10 @@ struct Wkv7BwdArgs {
     int B, T, H;
     const float* s;
     uint16_t *dw, *dq, *dk, *dv, *da, *db;
+    // segment-parallel mode (wkv7_chunk_dstate.cuh provides the boundary values): blockIdx.z = segment of `span`
+    // 16-step chunks, ds_in[b][h][segment][i][j] = dL/dS at the END of that segment (the last segment starts from 0)
+    const float* ds_in = nullptr;
+    int span = 0;  // 0: one CTA walks the whole sequence
 };
 
 }  // namespace vrwkv

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include <cudaTypedefs.h>
@@ -11,6 +12,8 @@
 #include "host_util.h"
 #include "wkv7_fwd.cuh"
 #include "wkv7_bwd2.cuh"
+#include "wkv7_chunk_fwd.cuh"
+#include "wkv7_chunk_dstate.cuh"
 #include "wkv7_fwd2.cuh"
 
 using namespace vrwkv;
@@ -54,6 +57,80 @@ static int launch_bwd2(const CUtensorMap* tm, const Wkv7BwdArgs& a, cudaStream_t
     return VRWKV_OK;
 }
 
+extern "C" int vrwkv_wkv7_chunk_debug(float* buf) {
+    VRWKV_CUDA(cudaMemcpyToSymbol(g_chunk_dbg, &buf, sizeof(buf)));
+    return VRWKV_OK;
+}
+
+static int launch_chunk_fwd(const void* const* in, const Wkv7FwdArgs& a, cudaStream_t st) {
+    CUtensorMap tm[6];
+    for (int i = 0; i < 6; i++) {
+        int rc = vrwkv_encode_2d(&tm[i], in[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)a.H * WKV_N, (uint64_t)a.B * a.T,
+                                 (uint64_t)a.H * WKV_N * 2, WKV_N, CK_L, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc) return rc;
+    }
+    const size_t smem = sizeof(Wkv7ChunkSmem) + 1024;
+    VRWKV_CUDA(cudaFuncSetAttribute(wkv7_chunk_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(a.H, a.B), block(CK_THREADS);
+    wkv7_chunk_fwd_kernel<<<grid, block, smem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], a);
+    VRWKV_CUDA(cudaGetLastError());
+    vrwkv_count_launch(1);
+    return VRWKV_OK;
+}
+
+static int make_chunk_map(CUtensorMap* m, const void* base, int B, int T, int H) {
+    return vrwkv_encode_2d(m, base, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)H * WKV_N, (uint64_t)B * T,
+                           (uint64_t)H * WKV_N * 2, WKV_N, CK_L, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
+// backward = tensor-core scan of dL/dS over 64-step chunks + the step-by-step kernel on all segments concurrently
+template <int R, int NSTAGE>
+static int launch_bwd_segmented(const CUtensorMap* tm, const void* w, const void* q, const void* a, const void* b,
+                                const void* dy, Wkv7BwdArgs args, cudaStream_t st) {
+    const int B = args.B, T = args.T, H = args.H, nseg = T / CK_L;
+    float* ds = nullptr;
+    if (nseg > 1) {
+        // stream-ordered workspace; keep freed blocks in the device's pool instead of returning them to the OS at
+        // every synchronisation (the default release threshold of 0 makes each step pay a real cudaMalloc)
+        static std::atomic<unsigned> pool_ready{0};
+        int dev = 0;
+        VRWKV_CUDA(cudaGetDevice(&dev));
+        if (!(pool_ready.load() & (1u << dev))) {
+            cudaMemPool_t pool;
+            VRWKV_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+            uint64_t keep = UINT64_MAX;
+            VRWKV_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+            pool_ready.fetch_or(1u << dev);
+        }
+        VRWKV_CUDA(cudaMallocAsync((void**)&ds, (size_t)B * H * nseg * WKV_N * WKV_N * sizeof(float), st));
+        CUtensorMap cm[5];
+        const void* in[5] = {w, q, a, b, dy};
+        for (int i = 0; i < 5; i++) {
+            int rc = make_chunk_map(&cm[i], in[i], B, T, H);
+            if (rc) return rc;
+        }
+        const size_t smem = sizeof(Wkv7DstateSmem) + 1024;
+        VRWKV_CUDA(cudaFuncSetAttribute(wkv7_chunk_dstate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        Wkv7DstateArgs da{B, T, H, ds};
+        wkv7_chunk_dstate_kernel<<<dim3(H, B), CK_THREADS, smem, st>>>(cm[0], cm[1], cm[2], cm[3], cm[4], da);
+        VRWKV_CUDA(cudaGetLastError());
+        vrwkv_count_launch(1);
+    }
+    args.ds_in = ds;
+    args.span = CK_L / WKV_TC;
+    auto kern = wkv7_bwd2_kernel<R, NSTAGE, 2>;
+    const size_t smem2 = sizeof(Wkv7Bwd2Smem<NSTAGE>) + 128;
+    VRWKV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    // two CTAs (2 x ~81 KB) per SM: ask for the largest shared-memory carveout, the default sizes it for one block
+    VRWKV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    dim3 grid(H, B, nseg), block((WKV_N / R) * 8 + 32);
+    kern<<<grid, block, smem2, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], tm[7], args);
+    VRWKV_CUDA(cudaGetLastError());
+    vrwkv_count_launch(1);
+    if (ds) VRWKV_CUDA(cudaFreeAsync(ds, st));
+    return VRWKV_OK;
+}
+
 static int check_common(int B, int T, int H, const void* const* ptrs, int nptr) {
     if (B <= 0 || T <= 0 || H <= 0) return vrwkv_fail(VRWKV_EINVAL, "wkv7: B,T,H must be positive (got %d,%d,%d)", B, T, H);
     if ((long long)B * T >= (1ll << 31)) return vrwkv_fail(VRWKV_EUNSUP, "wkv7: B*T too large");
@@ -64,9 +141,25 @@ static int check_common(int B, int T, int H, const void* const* ptrs, int nptr) 
     return VRWKV_OK;
 }
 
-extern "C" int vrwkv_wkv7_forward_state(int B, int T, int H, const uint16_t* w, const uint16_t* q, const uint16_t* k,
-                                        const uint16_t* v, const uint16_t* a, const uint16_t* b, uint16_t* y, float* s,
-                                        float* sa, const float* state_in, float* state_out, void* stream) {
+static unsigned default_flags() {  // VRWKV_WKV7_BOUNDED_DECAY=1 lets the drop-in op use the chunked kernels too
+    static const unsigned f = [] {
+        const char* e = getenv("VRWKV_WKV7_BOUNDED_DECAY");
+        return (e && e[0] == '1') ? (unsigned)VRWKV_WKV7_BOUNDED_DECAY : 0u;
+    }();
+    return f;
+}
+
+extern "C" int vrwkv_wkv7_domain_check(void) {
+    int flag = 0, zero = 0;
+    VRWKV_CUDA(cudaMemcpyFromSymbol(&flag, g_chunk_domain_err, sizeof(int)));
+    if (flag) VRWKV_CUDA(cudaMemcpyToSymbol(g_chunk_domain_err, &zero, sizeof(int)));
+    return flag ? vrwkv_fail(VRWKV_EINVAL, "wkv7 chunked kernels: sum over a 64-step chunk of exp(w) exceeded 80 "
+                                           "(VRWKV_WKV7_BOUNDED_DECAY promised exp(w) <= 0.607)") : VRWKV_OK;
+}
+
+extern "C" int vrwkv_wkv7_forward_ex(int B, int T, int H, const uint16_t* w, const uint16_t* q, const uint16_t* k,
+                                     const uint16_t* v, const uint16_t* a, const uint16_t* b, uint16_t* y, float* s,
+                                     float* sa, const float* state_in, float* state_out, unsigned flags, void* stream) {
     const void* ptrs[] = {w, q, k, v, a, b, y};
     int rc = check_common(B, T, H, ptrs, 7);
     if (rc) return rc;
@@ -81,12 +174,20 @@ extern "C" int vrwkv_wkv7_forward_state(int B, int T, int H, const uint16_t* w, 
     Wkv7FwdArgs args{B, T, H, y, s, sa, state_in, state_out};
     cudaStream_t st = (cudaStream_t)stream;
     int var = g_fwd_variant.load();
-    if (var == 0) var = 1;
+    if (var == 0) var = ((flags | default_flags()) & VRWKV_WKV7_BOUNDED_DECAY) ? 3 : 1;
+    if (var == 3 && (T % CK_L) != 0) var = 1;  // the chunked kernel walks 64 steps at a time
     switch (var) {
+        case 3: return launch_chunk_fwd(in, args, st);  // tensor-core chunked evaluation (needs sum_chunk exp(w) < ~85)
         case 1: return launch_fwd2<4, 4>(tm, args, st);  // 4 rows x 8 columns per thread, 4 compute warps
         case 2: return launch_fwd2<2, 4>(tm, args, st);  // 2 rows x 8 columns per thread, 8 compute warps
         default: return vrwkv_fail(VRWKV_EINVAL, "wkv7 forward: unknown variant %d", var);
     }
+}
+
+extern "C" int vrwkv_wkv7_forward_state(int B, int T, int H, const uint16_t* w, const uint16_t* q, const uint16_t* k,
+                                        const uint16_t* v, const uint16_t* a, const uint16_t* b, uint16_t* y, float* s,
+                                        float* sa, const float* state_in, float* state_out, void* stream) {
+    return vrwkv_wkv7_forward_ex(B, T, H, w, q, k, v, a, b, y, s, sa, state_in, state_out, 0u, stream);
 }
 
 extern "C" int vrwkv_wkv7_forward(int B, int T, int H, const uint16_t* w, const uint16_t* q, const uint16_t* k,
@@ -97,10 +198,10 @@ extern "C" int vrwkv_wkv7_forward(int B, int T, int H, const uint16_t* w, const 
     return vrwkv_wkv7_forward_state(B, T, H, w, q, k, v, a, b, y, s, sa, nullptr, nullptr, stream);
 }
 
-extern "C" int vrwkv_wkv7_backward(int B, int T, int H, const uint16_t* w, const uint16_t* q, const uint16_t* k,
-                                   const uint16_t* v, const uint16_t* a, const uint16_t* b, const uint16_t* dy,
-                                   const float* s, const float* sa, uint16_t* dw, uint16_t* dq, uint16_t* dk,
-                                   uint16_t* dv, uint16_t* da, uint16_t* db, void* stream) {
+extern "C" int vrwkv_wkv7_backward_ex(int B, int T, int H, const uint16_t* w, const uint16_t* q, const uint16_t* k,
+                                      const uint16_t* v, const uint16_t* a, const uint16_t* b, const uint16_t* dy,
+                                      const float* s, const float* sa, uint16_t* dw, uint16_t* dq, uint16_t* dk,
+                                      uint16_t* dv, uint16_t* da, uint16_t* db, unsigned flags, void* stream) {
     const void* ptrs[] = {w, q, k, v, a, b, dy, s, sa, dw, dq, dk, dv, da, db};
     int rc = check_common(B, T, H, ptrs, 15);
     if (rc) return rc;
@@ -113,10 +214,19 @@ extern "C" int vrwkv_wkv7_backward(int B, int T, int H, const uint16_t* w, const
     Wkv7BwdArgs args{B, T, H, s, dw, dq, dk, dv, da, db};
     cudaStream_t st = (cudaStream_t)stream;
     int var = g_bwd_variant.load();
-    if (var == 0) var = 1;
+    if (var == 0) var = ((flags | default_flags()) & VRWKV_WKV7_BOUNDED_DECAY) ? 3 : 1;
+    if (var == 3 && (T % CK_L) != 0) var = 1;
     switch (var) {
+        case 3: return launch_bwd_segmented<4, 3>(tm, w, q, a, b, dy, args, st);  // needs sum_chunk exp(w) < ~85
         case 1: return launch_bwd2<4, 3>(tm, args, st);
         case 2: return launch_bwd2<2, 3>(tm, args, st);
         default: return vrwkv_fail(VRWKV_EINVAL, "wkv7 backward: unknown variant %d", var);
     }
+}
+
+extern "C" int vrwkv_wkv7_backward(int B, int T, int H, const uint16_t* w, const uint16_t* q, const uint16_t* k,
+                                   const uint16_t* v, const uint16_t* a, const uint16_t* b, const uint16_t* dy,
+                                   const float* s, const float* sa, uint16_t* dw, uint16_t* dq, uint16_t* dk,
+                                   uint16_t* dv, uint16_t* da, uint16_t* db, void* stream) {
+    return vrwkv_wkv7_backward_ex(B, T, H, w, q, k, v, a, b, dy, s, sa, dw, dq, dk, dv, da, db, 0u, stream);
 }

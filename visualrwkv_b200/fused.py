@@ -161,20 +161,13 @@ def relu_sq_backward_from_act(act, dy):
 
 
 def wkv7_fwd_raw(w, q, k, v, a, b):
-    """[B,T,H,64] bf16 x6 -> y, s, sa through torch.ops.wind_backstepping (timed when wkv7.PROFILE is set)."""
-    _lib.load_torch_ops()
-    B, T, H, C = w.shape
-    y = torch.empty_like(v)
-    s = torch.empty(B, H, T // 16, C, C, dtype=torch.float32, device=w.device)
-    sa = torch.empty(B, T, H, C, dtype=torch.float32, device=w.device)
-    _wkv7._timed("fwd", lambda: torch.ops.wind_backstepping.forward(w, q, k, v, a, b, y, s, sa))
-    return y, s, sa
+    """[B,T,H,64] bf16 x6 -> y, s, sa.  The fused time-mix block builds w = -softplus(.) - 0.5 itself
+    (tmix_mid_fwd_kernel, model.py:176), so it may promise bounded decay (include/vrwkv_b200.h)."""
+    return _wkv7.forward_raw(w, q, k, v, a, b, bounded_decay=True)
 
 
 def wkv7_bwd_raw(w, q, k, v, a, b, dy, s, sa):
-    outs = [torch.empty_like(w) for _ in range(6)]
-    _wkv7._timed("bwd", lambda: torch.ops.wind_backstepping.backward(w, q, k, v, a, b, dy, s, sa, *outs))
-    return outs  # dw, dq, dk, dv, da, db
+    return _wkv7.backward_raw(w, q, k, v, a, b, dy, s, sa, bounded_decay=True)  # dw, dq, dk, dv, da, db
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -38,6 +38,72 @@ def launch_count() -> int:
     return int(L.vrwkv_launch_count())
 
 
+BOUNDED_DECAY = 1  # include/vrwkv_b200.h: VRWKV_WKV7_BOUNDED_DECAY
+
+
+def forward_raw(w, q, k, v, a, b, bounded_decay: bool = False):
+    """[B,T,H,64] bf16 x6 (kernel order) -> y, s, sa through the C ABI (vrwkv_wkv7_forward_ex).
+
+    bounded_decay=True is the caller's promise that exp(w) <= 0.607 (RWKV-7's w = -softplus(.) - 0.5, model.py:176);
+    it lets the library use the chunked tensor-core kernels."""
+    L = _lib.lib()
+    B, T, H, C = w.shape
+    assert C == 64 and T % CHUNK_LEN == 0
+    assert all(i.dtype == torch.bfloat16 and i.is_contiguous() and i.is_cuda for i in [w, q, k, v, a, b])
+    y = torch.empty_like(v)
+    s = torch.empty(B, H, T // CHUNK_LEN, C, C, dtype=torch.float32, device=w.device)
+    sa = torch.empty(B, T, H, C, dtype=torch.float32, device=w.device)
+
+    def run():
+        with torch.cuda.device(w.device):
+            rc = L.vrwkv_wkv7_forward_ex(B, T, H, _lib.ptr(w), _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(a),
+                                         _lib.ptr(b), _lib.ptr(y), _lib.ptr(s), _lib.ptr(sa), None, None,
+                                         ctypes.c_uint(BOUNDED_DECAY if bounded_decay else 0), _lib.cur_stream())
+        _lib.check(rc, "vrwkv_wkv7_forward_ex")
+
+    _timed("fwd", run)
+    return y, s, sa
+
+
+def backward_raw(w, q, k, v, a, b, dy, s, sa, bounded_decay: bool = False):
+    """Returns dw, dq, dk, dv, da, db (bf16 [B,T,H,64]) through vrwkv_wkv7_backward_ex."""
+    L = _lib.lib()
+    B, T, H, C = w.shape
+    assert dy.dtype == torch.bfloat16 and dy.is_contiguous()
+    outs = [torch.empty_like(w) for _ in range(6)]
+
+    def run():
+        with torch.cuda.device(w.device):
+            rc = L.vrwkv_wkv7_backward_ex(B, T, H, _lib.ptr(w), _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(a),
+                                          _lib.ptr(b), _lib.ptr(dy), _lib.ptr(s), _lib.ptr(sa),
+                                          *[_lib.ptr(o) for o in outs],
+                                          ctypes.c_uint(BOUNDED_DECAY if bounded_decay else 0), _lib.cur_stream())
+        _lib.check(rc, "vrwkv_wkv7_backward_ex")
+
+    _timed("bwd", run)
+    return outs
+
+
+def domain_check() -> None:
+    """Synchronises; raises if a chunked kernel met decay outside the range promised by bounded_decay=True."""
+    _lib.check(_lib.lib().vrwkv_wkv7_domain_check(), "vrwkv_wkv7_domain_check")
+
+
+class WindBacksteppingBounded(torch.autograd.Function):
+    """WindBackstepping for callers that build w the RWKV-7 way (exp(w) <= 0.607): chunked tensor-core kernels."""
+
+    @staticmethod
+    def forward(ctx, w, q, k, v, z, b):
+        y, s, sa = forward_raw(w, q, k, v, z, b, bounded_decay=True)
+        ctx.save_for_backward(w, q, k, v, z, b, s, sa)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        w, q, k, v, z, b, s, sa = ctx.saved_tensors
+        return tuple(backward_raw(w, q, k, v, z, b, dy.contiguous(), s, sa, bounded_decay=True))
+
+
 class WindBackstepping(torch.autograd.Function):
     """model.py:45-65 — same ops, same allocations, same saved tensors."""
 
@@ -65,11 +131,14 @@ class WindBackstepping(torch.autograd.Function):
         return dw, dq, dk, dv, dz, db
 
 
-def RUN_CUDA_RWKV7g(q, w, k, v, a, b):
-    """model.py:67-70: six [B,T,H*64] bf16 -> [B,T,H*64] bf16, differentiable in all six."""
+def RUN_CUDA_RWKV7g(q, w, k, v, a, b, bounded_decay: bool = False):
+    """model.py:67-70: six [B,T,H*64] bf16 -> [B,T,H*64] bf16, differentiable in all six.
+
+    bounded_decay=True (not in the reference signature): w was built as -softplus(.) - 0.5, see forward_raw."""
     B, T, HC = q.shape
     q, w, k, v, a, b = [i.view(B, T, HC // 64, 64) for i in [q, w, k, v, a, b]]
-    return WindBackstepping.apply(w, q, k, v, a, b).view(B, T, HC)
+    fn = WindBacksteppingBounded if bounded_decay else WindBackstepping
+    return fn.apply(w, q, k, v, a, b).view(B, T, HC)
 
 
 def wkv7_forward_state(w, q, k, v, a, b, state_in=None, want_checkpoints: bool = False):
