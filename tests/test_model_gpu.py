@@ -94,9 +94,22 @@ def test_scatter_is_bit_exact_and_ordered():
     # fewer slots than features: the reference truncates the features (model.py:487-491)
     ids2 = ids.clone()
     ids2[2, 4:8] = 7
-    with pytest.warns(UserWarning):
-        x2 = ops.embed_and_scatter(emb, ids2, feats, 65535)
+    x2 = ops.embed_and_scatter(emb, ids2, feats, 65535)
     assert torch.equal(x2[0, 3:11], feats[0]) and torch.equal(x2[2, 0:4], feats[1][:4])
+    assert torch.equal(x2[2, 4:8], emb[ids2[2, 4:8]])
+    with pytest.warns(UserWarning):  # the count check is deferred (no host sync inside the forward)
+        ops.flush_checks()
+    # more slots than features is an error in the reference (index_put shape mismatch); here it is raised late too
+    ids3 = ids.clone()
+    ids3[1, 0:4] = 65535
+    ops.embed_and_scatter(emb, ids3, feats, 65535)
+    with pytest.warns(UserWarning), pytest.raises(RuntimeError):
+        ops.flush_checks()
+    # gradient reaches exactly the gathered feature rows
+    f = feats.clone().float().requires_grad_(True)
+    ops.embed_and_scatter(emb.float(), ids, f, 65535).sum().backward()
+    ops.flush_checks()
+    assert torch.equal(f.grad, torch.full_like(f, 1.0))
 
 
 def test_vit_matches_hf_siglip_on_gpu():

@@ -365,29 +365,39 @@ __global__ void __launch_bounds__(256) relu_sq_bwd_from_act_kernel(const uint16_
 }
 
 // second stage of the per-channel parameter gradients: out[i] (bf16) = sum over blocks of partial[blk][i], i in [0, n*C).
-// CTA = 64 column groups (4 consecutive columns each, float4 loads) x 4 slices of the block range; the slices are
-// combined through shared memory.  ~100 CTAs, every load coalesced: the 6-25 MB of partials stream in a few microseconds.
+// CTA = 8 column groups (4 consecutive columns each: one 128-byte line per block row) x 32 slices of the block range,
+// 8 independent 16-byte loads in flight per thread; the slices are combined through shared memory.  A [512, 6144]
+// array of partials becomes 192 CTAs with ~6 MB in flight instead of 24 CTAs walking 128 rows each.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* partial, uint16_t* out, int nb, int nc) {
-    __shared__ float4 red[4][64];
-    const int cg = threadIdx.x & 63, slice = threadIdx.x >> 6;
-    const int col = (blockIdx.x * 64 + cg) * 4;
+    __shared__ float4 red[32][8];
+    const int cg = threadIdx.x & 7, slice = threadIdx.x >> 3;
+    const int col = (blockIdx.x * 8 + cg) * 4;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (col < nc) {
-        float4 s2 = make_float4(0.f, 0.f, 0.f, 0.f);
-        int b = slice;
-        for (; b + 4 < nb; b += 8) {
-            const float4 x = *reinterpret_cast<const float4*>(partial + (size_t)b * nc + col);
-            const float4 y = *reinterpret_cast<const float4*>(partial + (size_t)(b + 4) * nc + col);
-            s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
-            s2.x += y.x; s2.y += y.y; s2.z += y.z; s2.w += y.w;
+        for (int b0 = slice; b0 < nb; b0 += 32 * 8) {
+            float4 x[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int b = b0 + 32 * u;
+                x[u] = (b < nb) ? __ldg(reinterpret_cast<const float4*>(partial + (size_t)b * nc + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                s.x += x[u].x; s.y += x[u].y; s.z += x[u].z; s.w += x[u].w;
+            }
         }
-        for (; b < nb; b += 4) {
-            const float4 x = *reinterpret_cast<const float4*>(partial + (size_t)b * nc + col);
-            s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
-        }
-        s.x += s2.x; s.y += s2.y; s.z += s2.z; s.w += s2.w;
     }
     red[slice][cg] = s;
+    __syncthreads();
+    if (slice < 4) {  // 32 -> 4 -> 1
+        float4 t = red[slice][cg];
+#pragma unroll
+        for (int k = 1; k < 8; k++) {
+            const float4 o = red[slice + 4 * k][cg];
+            t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+        }
+        red[slice][cg] = t;
+    }
     __syncthreads();
     if (slice == 0 && col < nc) {
         float4 t = red[0][cg];
@@ -515,7 +525,7 @@ extern "C" int vrwkv_relu_sq_backward_from_act(size_t n, const uint16_t* y, cons
 extern "C" int vrwkv_reduce_partials(int nblocks, int n_times_c, const float* partial, uint16_t* out, void* stream) {
     if (nblocks <= 0 || n_times_c <= 0 || !partial || !out) return vrwkv_fail(VRWKV_EINVAL, "reduce_partials: bad arguments");
     if (n_times_c % 4) return vrwkv_fail(VRWKV_EINVAL, "reduce_partials: n*C must be a multiple of 4");
-    reduce_partials_kernel<<<(n_times_c / 4 + 63) / 64, 256, 0, (cudaStream_t)stream>>>(partial, out, nblocks, n_times_c);
+    reduce_partials_kernel<<<(n_times_c / 4 + 7) / 8, 256, 0, (cudaStream_t)stream>>>(partial, out, nblocks, n_times_c);
     VRWKV_CUDA(cudaGetLastError());
     vrwkv_count_launch(1);
     return VRWKV_OK;

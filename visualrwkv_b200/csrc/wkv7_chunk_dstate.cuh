@@ -16,9 +16,7 @@
 // fp32 on the CUDA cores exactly as in the forward kernel.  Output: ds[b][h][c][i][j] = dL/dS at the end of chunk c
 // for c = 0 .. T/64 - 2 (the last chunk ends the sequence: zero, not stored).
 #pragma once
-#include "common.cuh"
-#include "umma.cuh"
-#include "wkv7_chunk_fwd.cuh"
+#include "wkv7_chunk_common.cuh"
 
 namespace vrwkv {
 
@@ -199,6 +197,8 @@ wkv7_chunk_dstate_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
         }
         mma_wait();
         // ================= P2: A_ab (fp32, for the inverse) and A_qb (operand) =================
+        *reinterpret_cast<float4*>(sm.tinv + tid * 32) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(sm.tinv + tid * 32 + 16) = make_float4(0.f, 0.f, 0.f, 0.f);
         {
             uint32_t v[16];
             tmem_ld16(tm_row + C_SC + 16 * cs, v);
@@ -232,69 +232,8 @@ wkv7_chunk_dstate_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
             for (int k = 0; k < 8; k++) umma_tf32(tmem + C_U, umma_desc_advance(da, k * 1024), umma_desc_advance(db, k * 1024), ID_MM, 1);
             umma_commit(&sm.bar_mma);
         }
-        // ---- I1: inverses of the two 32x32 diagonal blocks of T = I - A_ab ----
-        if (warp < 2) {
-            const int bl = warp, cc = lane;
-            float x[32];
-#pragma unroll
-            for (int t = 0; t < 32; t++) {
-                float a0 = (t == cc) ? 1.f : 0.f, a1 = 0.f;
-#pragma unroll
-                for (int c4 = 0; c4 < (t + 3) / 4; c4++) {
-                    const float4 m = *reinterpret_cast<const float4*>(sm.aab + (32 * bl + t) * 256 + (((8 * bl + c4) ^ (t & 7)) << 4));
-                    const float mm[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const int s = 4 * c4 + e;
-                        if (s < t) {
-                            if (s & 1) a1 = fmaf(mm[e], x[s], a1);
-                            else a0 = fmaf(mm[e], x[s], a0);
-                        }
-                    }
-                }
-                x[t] = a0 + a1;
-                *reinterpret_cast<float*>(sm.tinv + bl * 8192 + sw32_off(32 * bl + t, cc)) = rt32(x[t]);
-            }
-        } else if (warp < 10) {
-            const int z = tid - 64;  // zero Tinv rows 0-31, columns 32-63
-            *reinterpret_cast<float4*>(sm.tinv + 8192 + z * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        __syncthreads();
-        // ---- I2: E = A_c X_a ----
-        {
-            const int t = tid >> 4, c0 = 2 * (tid & 15);
-            float e0 = 0.f, e1 = 0.f;
-#pragma unroll
-            for (int c4 = 0; c4 < 8; c4++) {
-                const float4 m = *reinterpret_cast<const float4*>(sm.aab + (32 + t) * 256 + ((c4 ^ (t & 7)) << 4));
-                const float mm[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const float2 xa = *reinterpret_cast<const float2*>(sm.tinv + sw32_off(4 * c4 + e, c0));
-                    e0 = fmaf(mm[e], xa.x, e0);
-                    e1 = fmaf(mm[e], xa.y, e1);
-                }
-            }
-            *reinterpret_cast<float2*>(&sm.esc[t * 32 + c0]) = make_float2(e0, e1);
-        }
-        __syncthreads();
-        // ---- I3: X_c = X_b E -> Tinv rows 32-63, columns 0-31 ----
-        {
-            const int t = tid >> 4, c0 = 2 * (tid & 15);
-            float e0 = 0.f, e1 = 0.f;
-#pragma unroll
-            for (int c4 = 0; c4 < 8; c4++) {
-                const float4 m = *reinterpret_cast<const float4*>(sm.tinv + 8192 + sw32_off(32 + t, 4 * c4));
-                const float mm[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const float2 ev = *reinterpret_cast<const float2*>(&sm.esc[(4 * c4 + e) * 32 + c0]);
-                    e0 = fmaf(mm[e], ev.x, e0);
-                    e1 = fmaf(mm[e], ev.y, e1);
-                }
-            }
-            *reinterpret_cast<float2*>(sm.tinv + sw32_off(32 + t, c0)) = make_float2(rt32(e0), rt32(e1));
-        }
+        // ---- Tinv = (I - A_ab)^-1, written row-major [t][s] in the MN-major operand layout ----
+        chunk_tri_inverse(sm.aab, sm.esc, tid, [&](int t, int s) { return sm.tinv + (s >> 5) * 8192 + sw32_off(t, s & 31); });
         mma_wait();
         // ================= dU -> operand =================
         if (r < 64) {

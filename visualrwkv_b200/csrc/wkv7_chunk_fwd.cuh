@@ -7,11 +7,11 @@
 // -exp(w) inside the chunk and  At = a exp(G_{t-1}), Qt = q exp(G_t), Kt = k exp(-G_t), Bt = b exp(-G_t):
 //   scores  = [At;Qt] [Bt;Kt]^T      (128x128x64)  -> A_ab, A_ak (strictly lower), A_qb, A_qk (lower triangular)
 //   ACC     = [A_ak;A_qk] V          (128x64x64)   rows 0-63: AV
-//   Tinv    = (I - A_ab)^-1          fp32 on the CUDA cores: two 32x32 triangular inverses + the coupling block
+//   Tinv    = (I - A_ab)^-1          fp32 on the CUDA cores (chunk_tri_inverse: 16x16 blocks + two coupling levels)
 //   TX      = Tinv [At | AV]         (64x128x64)   = [Ah | Uh]
 //   CORR    = [A_ab;A_qb] Ah ;  ACC += [A_ab;A_qb] Uh          => [At;Qt] + CORR = [Ah;Qp],  ACC = [Uh; Y_intra]
 //   ACC    += [Ah;Qp] S_0^T                                    => ACC = [U; Y]  (rows of U are the sa_t)
-//   STATE  += U^T Bt + V^T Kt  in four 16-step groups (checkpoint after each), then S_L = STATE diag(exp(G_L))
+//   D_g     = U_g^T Bt_g + V_g^T Kt_g for the four 16-step groups g; S_{16(g+1)} = (S_0 + D_0 + .. + D_g) diag(exp(G))
 // Operand layouts: K-major operands use SWIZZLE_128B rows of 32 tf32; [Bt;Kt], [U;V] and [At|AV] -> [Ah|Uh] are
 // stored row-major [step][channel] in the SWIZZLE_128B_BASE32B layout and consumed MN-major, so nothing is transposed
 // by hand.  Every MMA is issued by thread 0 and followed by a commit that all threads wait for (the phases are
@@ -20,17 +20,9 @@
 // w = -softplus(.) - 0.5 (exp(w) <= 0.607, model.py:176); the host dispatcher keeps the step-by-step kernel for
 // callers that cannot promise that.
 #pragma once
-#include "common.cuh"
-#include "umma.cuh"
-#include "wkv7_fwd.cuh"
+#include "wkv7_chunk_common.cuh"
 
 namespace vrwkv {
-
-constexpr int CK_L = 64;        // steps per chunk
-constexpr int CK_THREADS = 512;
-
-__device__ int g_chunk_domain_err = 0;    // set when a chunk's accumulated decay leaves the fp32-safe range
-__device__ float* g_chunk_dbg = nullptr;  // development aid: when set, CTA (0,0) records per-phase clocks of chunk 1
 
 struct alignas(1024) Wkv7ChunkSmem {
     uint8_t in[6 * CK_L * WKV_N * 2];  // TMA tiles w,q,k,v,a,b [64][64] bf16; later RMN (32 KB) and TINV (16 KB)
@@ -43,6 +35,7 @@ struct alignas(1024) Wkv7ChunkSmem {
     float esc[32 * 32];                // coupling-block scratch of the inverse
     float part[8][WKV_N];              // per row-group decay sums
     float echk[4][WKV_N];              // exp(G_t) at t = 15, 31, 47, 63
+    float eck[4][WKV_N];               // the same for the previous chunk (its checkpoints are written one chunk late)
     uint64_t bar_in, bar_mma;
     uint32_t tmem_base;
 };
@@ -82,7 +75,9 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
     const uint32_t tm_row = tmem + ((uint32_t)(32 * qd) << 16);
-    constexpr uint32_t C_SC = 0, C_UY = 128, C_CORR = 192, C_ST = 256, C_TX = 320;
+    constexpr uint32_t C_SC = 0, C_UY = 128, C_CORR = 192, C_TX = 320;
+    // partial state sums of the four 16-step groups reuse the score / TX columns (both are dead by then)
+    constexpr uint32_t C_R0 = 0, C_R1 = 64, C_R2 = 320, C_R3 = 384;
 
     auto issue_loads = [&](int c) {
         mbar_arrive_expect_tx(&sm.bar_in, 6 * L * N * 2);
@@ -98,30 +93,25 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
     __syncwarp();
     float* const dbg = (hh == 0 && bb == 0) ? g_chunk_dbg : nullptr;
 
-    // ---- initial state: STATE accumulator (fp32) and its tf32 image as the B operand of the first chunk ----
-    if (r < N) {  // row i = r, columns 16cs .. 16cs+15
-        uint32_t v[16];
+    // ---- initial state: fp32 in registers (thread r < 64 holds S[r][16cs .. 16cs+15]) + tf32 image as B operand ----
+    float Sprev[16];
+#pragma unroll
+    for (int e = 0; e < 16; e++) Sprev[e] = 0.f;
+    if (r < N) {
         if (p.state_in) {
             const float4* src = reinterpret_cast<const float4*>(p.state_in + (((size_t)bb * H + hh) * N + r) * N + 16 * cs);
 #pragma unroll
             for (int c4 = 0; c4 < 4; c4++) {
                 const float4 x = __ldg(src + c4);
-                v[4 * c4] = __float_as_uint(x.x); v[4 * c4 + 1] = __float_as_uint(x.y);
-                v[4 * c4 + 2] = __float_as_uint(x.z); v[4 * c4 + 3] = __float_as_uint(x.w);
+                Sprev[4 * c4] = x.x; Sprev[4 * c4 + 1] = x.y; Sprev[4 * c4 + 2] = x.z; Sprev[4 * c4 + 3] = x.w;
             }
-        } else {
-#pragma unroll
-            for (int e = 0; e < 16; e++) v[e] = 0u;
         }
-        tmem_st16(tm_row + C_ST + 16 * cs, v);
 #pragma unroll
         for (int c4 = 0; c4 < 4; c4++) {
             const int ch = 4 * (cs & 1) + c4;
             *reinterpret_cast<float4*>(sm.sb + (cs >> 1) * 8192 + r * 128 + ((ch ^ (r & 7)) << 4)) =
-                rt32(make_float4(__uint_as_float(v[4 * c4]), __uint_as_float(v[4 * c4 + 1]), __uint_as_float(v[4 * c4 + 2]),
-                                 __uint_as_float(v[4 * c4 + 3])));
+                rt32(make_float4(Sprev[4 * c4], Sprev[4 * c4 + 1], Sprev[4 * c4 + 2], Sprev[4 * c4 + 3]));
         }
-        tmem_st_wait();
     }
     fence_proxy_async();
     tc_fence_before();
@@ -155,8 +145,36 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
                        ID_B_MN_64 = umma_idesc_tf32(128, 64, 0, 1), ID_B_MN_128 = umma_idesc_tf32(128, 128, 0, 1),
                        ID_ST = umma_idesc_tf32(128, 64, 1, 1);
 
+    // checkpoints of chunk c-1: written at the start of chunk c so that the stores drain behind P1 instead of in
+    // front of the end-of-chunk fence; the four partial-state regions stay valid until the next score product
+    float Sck[16];  // state at the start of the chunk whose checkpoints are still to be written
+#pragma unroll
+    for (int e = 0; e < 16; e++) Sck[e] = 0.f;
+    auto write_checkpoints = [&](int c) {
+        if (p.s == nullptr || r >= N) return;
+        uint32_t v0[16], v1[16], v2[16], v3[16];
+        tmem_ld16_nowait(tm_row + C_R0 + 16 * cs, v0);
+        tmem_ld16_nowait(tm_row + C_R1 + 16 * cs, v1);
+        tmem_ld16_nowait(tm_row + C_R2 + 16 * cs, v2);
+        tmem_ld16_nowait(tm_row + C_R3 + 16 * cs, v3);
+        tmem_ld_wait();
+        float* ck = p.s + ((((size_t)bb * H + hh) * (T / WKV_TC) + (size_t)c * 4) * N + 16 * cs) * N + r;
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            float acc = Sck[e] + __uint_as_float(v0[e]);
+            ck[(size_t)e * N] = acc * sm.eck[0][16 * cs + e];  // transposed checkpoint [j][i] (wkv7_cuda.cu:44-50)
+            acc += __uint_as_float(v1[e]);
+            ck[(size_t)(N + e) * N] = acc * sm.eck[1][16 * cs + e];
+            acc += __uint_as_float(v2[e]);
+            ck[(size_t)(2 * N + e) * N] = acc * sm.eck[2][16 * cs + e];
+            acc += __uint_as_float(v3[e]);
+            ck[(size_t)(3 * N + e) * N] = acc * sm.eck[3][16 * cs + e];
+        }
+    };
+
     for (int c = 0; c < nch; c++) {
         stamp(c);
+        if (c > 0) write_checkpoints(c - 1);
         mbar_wait(&sm.bar_in, c & 1);
         stamp(c);
         // ================= P1: decay prefix sums and scaled operands (8 rows x 1 column per thread) =================
@@ -216,6 +234,8 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
         }
         mma_wait(c);
         // ================= P2: masks; [A_ak;A_qk] operand; A_ab in fp32 for the inverse =================
+        *reinterpret_cast<float4*>(tinv + tid * 32) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(tinv + tid * 32 + 16) = make_float4(0.f, 0.f, 0.f, 0.f);
         float sc0[32];  // warps with cs < 2 keep their slice of [A_ab;A_qb] until the operand buffer is free again
         {
             uint32_t v[32];
@@ -254,44 +274,18 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
             }
             umma_commit(&sm.bar_mma);
         }
-        // ================= I1: inverses of the two 32x32 diagonal blocks of T = I - A_ab (one column per thread) ====
-        if (warp < 2) {
-            const int bl = warp, cc = lane;
-            float x[32];
+        // ================= At (K-major rows 0-63 of aq) -> rmn blocks 0,1 (MN-major, k-line = step) =================
+        {
+            const int t = tid >> 3, q8 = tid & 7;  // two 16-byte chunks per thread
 #pragma unroll
-            for (int t = 0; t < 32; t++) {
-                float a0 = (t == cc) ? 1.f : 0.f, a1 = 0.f;
-#pragma unroll
-                for (int c4 = 0; c4 < (t + 3) / 4; c4++) {
-                    const float4 m = *reinterpret_cast<const float4*>(sm.aab + (32 * bl + t) * 256 + (((8 * bl + c4) ^ (t & 7)) << 4));
-                    const float mm[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const int s = 4 * c4 + e;
-                        if (s < t) {
-                            if (s & 1) a1 = fmaf(mm[e], x[s], a1);
-                            else a0 = fmaf(mm[e], x[s], a0);
-                        }
-                    }
-                }
-                x[t] = a0 + a1;
-                *reinterpret_cast<float*>(tinv + bl * 8192 + sw128_off(32 * bl + t, cc)) = rt32(x[t]);
-            }
-        } else if (warp < 10) {
-            // zero the upper-right block of Tinv (rows 0-31, k 32-63): 32 rows x 128 B
-            const int z = tid - 64;  // 0..255
-            *reinterpret_cast<float4*>(tinv + 8192 + z * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else if (warp < 14) {
-            // At (K-major rows 0-63 of aq) -> rmn blocks 0,1 (MN-major, k-line = step)
-            const int z = tid - 320;            // 0..127
-            const int t = z >> 1, half = z & 1;  // 8 chunks of 16 B each
-#pragma unroll
-            for (int cc = 0; cc < 8; cc++) {
-                const int ch = 8 * half + cc;  // 16-byte chunk 0..15 of the 64-float row
+            for (int x = 0; x < 2; x++) {
+                const int ch = 2 * q8 + x;  // chunk 0..15 of the 64-float row
                 const float4 val = *reinterpret_cast<const float4*>(sm.aq + (ch >> 3) * 16384 + t * 128 + (((ch & 7) ^ (t & 7)) << 4));
                 *reinterpret_cast<float4*>(rmn + (ch >> 3) * 8192 + sw32_off(t, 4 * (ch & 7))) = val;
             }
         }
+        // ================= Tinv = (I - A_ab)^-1 =================
+        chunk_tri_inverse(sm.aab, sm.esc, tid, [&](int t, int s) { return tinv + (s >> 5) * 8192 + sw128_off(t, s & 31); });
         mma_wait(c);
         // ================= P3: AV -> rmn blocks 2,3; [A_ab;A_qb] operand =================
         if (r < 64) {
@@ -308,43 +302,6 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
             for (int cc = 0; cc < 8; cc++)
                 *reinterpret_cast<float4*>(sc + cs * 16384 + r * 128 + ((cc ^ (r & 7)) << 4)) =
                     rt32(make_float4(sc0[4 * cc], sc0[4 * cc + 1], sc0[4 * cc + 2], sc0[4 * cc + 3]));
-        }
-        __syncthreads();
-        // ================= I2: E = A_c X_a  (A_c = A_ab[32+t][s], X_a = Tinv rows/cols 0-31) =================
-        {
-            const int t = tid >> 4, c0 = 2 * (tid & 15);
-            float e0 = 0.f, e1 = 0.f;
-#pragma unroll
-            for (int c4 = 0; c4 < 8; c4++) {
-                const float4 m = *reinterpret_cast<const float4*>(sm.aab + (32 + t) * 256 + ((c4 ^ (t & 7)) << 4));
-                const float mm[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const int s = 4 * c4 + e;
-                    const float2 xa = *reinterpret_cast<const float2*>(tinv + sw128_off(s, c0));
-                    e0 = fmaf(mm[e], xa.x, e0);
-                    e1 = fmaf(mm[e], xa.y, e1);
-                }
-            }
-            *reinterpret_cast<float2*>(&sm.esc[t * 32 + c0]) = make_float2(e0, e1);
-        }
-        __syncthreads();
-        // ================= I3: X_c = X_b E  -> Tinv rows 32-63, k 0-31 =================
-        {
-            const int t = tid >> 4, c0 = 2 * (tid & 15);
-            float e0 = 0.f, e1 = 0.f;
-#pragma unroll
-            for (int c4 = 0; c4 < 8; c4++) {
-                const float4 m = *reinterpret_cast<const float4*>(tinv + 8192 + (32 + t) * 128 + ((c4 ^ (t & 7)) << 4));
-                const float mm[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const float2 ev = *reinterpret_cast<const float2*>(&sm.esc[(4 * c4 + e) * 32 + c0]);
-                    e0 = fmaf(mm[e], ev.x, e0);
-                    e1 = fmaf(mm[e], ev.y, e1);
-                }
-            }
-            *reinterpret_cast<float2*>(tinv + sw128_off(32 + t, c0)) = make_float2(rt32(e0), rt32(e1));
         }
         operands_ready();
         // ================= TX = Tinv [At | AV] =================
@@ -418,81 +375,88 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
             umma_commit(&sm.bar_mma);
         }
         mma_wait(c);
-        // ================= P6: sa and y to global memory; U operand =================
-        {
-            uint32_t v[16];
-            tmem_ld16(tm_row + C_UY + 16 * cs, v);
-            const size_t row = (((size_t)bb * T + (size_t)c * L + t_r) * H + hh) * N + 16 * cs;
-            if (r < 64) {
+        // ================= P6: U operand; then D_g = U_g^T Bt_g + V_g^T Kt_g; sa / y stores behind the barrier ====
+        uint32_t uy[16];
+        tmem_ld16(tm_row + C_UY + 16 * cs, uy);
+        if (r < 64) {
 #pragma unroll
-                for (int c4 = 0; c4 < 4; c4++) {
-                    const float4 u = make_float4(__uint_as_float(v[4 * c4]), __uint_as_float(v[4 * c4 + 1]),
-                                                 __uint_as_float(v[4 * c4 + 2]), __uint_as_float(v[4 * c4 + 3]));
-                    if (p.sa) *reinterpret_cast<float4*>(p.sa + row + 4 * c4) = u;
-                    *reinterpret_cast<float4*>(sm.uv + (cs >> 1) * 16384 + sw32_off(r, 16 * (cs & 1) + 4 * c4)) = rt32(u);
-                }
-            } else {
-                uint4 o0, o1;
-                o0.x = pack_bf16x2(__uint_as_float(v[0]), __uint_as_float(v[1]));
-                o0.y = pack_bf16x2(__uint_as_float(v[2]), __uint_as_float(v[3]));
-                o0.z = pack_bf16x2(__uint_as_float(v[4]), __uint_as_float(v[5]));
-                o0.w = pack_bf16x2(__uint_as_float(v[6]), __uint_as_float(v[7]));
-                o1.x = pack_bf16x2(__uint_as_float(v[8]), __uint_as_float(v[9]));
-                o1.y = pack_bf16x2(__uint_as_float(v[10]), __uint_as_float(v[11]));
-                o1.z = pack_bf16x2(__uint_as_float(v[12]), __uint_as_float(v[13]));
-                o1.w = pack_bf16x2(__uint_as_float(v[14]), __uint_as_float(v[15]));
-                *reinterpret_cast<uint4*>(p.y + row) = o0;
-                *reinterpret_cast<uint4*>(p.y + row + 8) = o1;
-            }
+            for (int c4 = 0; c4 < 4; c4++)
+                *reinterpret_cast<float4*>(sm.uv + (cs >> 1) * 16384 + sw32_off(r, 16 * (cs & 1) + 4 * c4)) =
+                    rt32(make_float4(__uint_as_float(uy[4 * c4]), __uint_as_float(uy[4 * c4 + 1]), __uint_as_float(uy[4 * c4 + 2]),
+                                     __uint_as_float(uy[4 * c4 + 3])));
         }
         operands_ready();
-        // ================= STATE += U^T Bt + V^T Kt, 16 steps at a time =================
-#pragma unroll 1
-        for (int g = 0; g < 4; g++) {
-            if (tid == 0) {
-                tc_fence_after();
-                const uint64_t da = umma_desc_mn_tf32(sm.uv, 16384, 512);
-                const uint64_t db = umma_desc_mn_tf32(sm.bk2, 16384, 512);
+        if (tid == 0) {
+            tc_fence_after();
+            const uint64_t da = umma_desc_mn_tf32(sm.uv, 16384, 512);
+            const uint64_t db = umma_desc_mn_tf32(sm.bk2, 16384, 512);
+            constexpr uint32_t creg[4] = {C_R0, C_R1, C_R2, C_R3};
+#pragma unroll
+            for (int g = 0; g < 4; g++)
 #pragma unroll
                 for (int part = 0; part < 2; part++)
 #pragma unroll
                     for (int x = 0; x < 2; x++) {
                         const uint32_t off = (uint32_t)(part * 64 + 16 * g + 8 * x) * 128;
-                        umma_tf32(tmem + C_ST, umma_desc_advance(da, off), umma_desc_advance(db, off), ID_ST, 1);
+                        umma_tf32(tmem + creg[g], umma_desc_advance(da, off), umma_desc_advance(db, off), ID_ST, (part | x) != 0);
                     }
-                umma_commit(&sm.bar_mma);
-            }
-            mma_wait(c);
-            if (r < 64) {  // row i = r, columns j = 16cs .. 16cs+15
-                uint32_t v[16];
-                tmem_ld16(tm_row + C_ST + 16 * cs, v);
-                float* ck = p.s ? p.s + ((((size_t)bb * H + hh) * (T / WKV_TC) + (size_t)c * 4 + g) * N + 16 * cs) * N + r : nullptr;
-                float sv[16];
-#pragma unroll
-                for (int e = 0; e < 16; e++) {
-                    sv[e] = __uint_as_float(v[e]) * sm.echk[g][16 * cs + e];
-                    if (ck) ck[(size_t)e * N] = sv[e];  // transposed checkpoint [j][i] (wkv7_cuda.cu:44-50)
-                }
-                if (g == 3) {
-#pragma unroll
-                    for (int e = 0; e < 16; e++) v[e] = __float_as_uint(sv[e]);
-                    tmem_st16(tm_row + C_ST + 16 * cs, v);
-#pragma unroll
-                    for (int c4 = 0; c4 < 4; c4++) {
-                        const int ch = 4 * (cs & 1) + c4;
-                        *reinterpret_cast<float4*>(sm.sb + (cs >> 1) * 8192 + r * 128 + ((ch ^ (r & 7)) << 4)) =
-                            rt32(make_float4(sv[4 * c4], sv[4 * c4 + 1], sv[4 * c4 + 2], sv[4 * c4 + 3]));
-                    }
-                    if (p.state_out && c == nch - 1) {
-                        float4* dst = reinterpret_cast<float4*>(p.state_out + (((size_t)bb * H + hh) * N + r) * N + 16 * cs);
-#pragma unroll
-                        for (int c4 = 0; c4 < 4; c4++) dst[c4] = make_float4(sv[4 * c4], sv[4 * c4 + 1], sv[4 * c4 + 2], sv[4 * c4 + 3]);
-                    }
-                    tmem_st_wait();
-                }
-            }
-            operands_ready();
+            umma_commit(&sm.bar_mma);
         }
+        {
+            const size_t row = (((size_t)bb * T + (size_t)c * L + t_r) * H + hh) * N + 16 * cs;
+            if (r < 64) {
+                if (p.sa) {
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; c4++)
+                        *reinterpret_cast<float4*>(p.sa + row + 4 * c4) =
+                            make_float4(__uint_as_float(uy[4 * c4]), __uint_as_float(uy[4 * c4 + 1]), __uint_as_float(uy[4 * c4 + 2]),
+                                        __uint_as_float(uy[4 * c4 + 3]));
+                }
+            } else {
+                uint4 o0, o1;
+                o0.x = pack_bf16x2(__uint_as_float(uy[0]), __uint_as_float(uy[1]));
+                o0.y = pack_bf16x2(__uint_as_float(uy[2]), __uint_as_float(uy[3]));
+                o0.z = pack_bf16x2(__uint_as_float(uy[4]), __uint_as_float(uy[5]));
+                o0.w = pack_bf16x2(__uint_as_float(uy[6]), __uint_as_float(uy[7]));
+                o1.x = pack_bf16x2(__uint_as_float(uy[8]), __uint_as_float(uy[9]));
+                o1.y = pack_bf16x2(__uint_as_float(uy[10]), __uint_as_float(uy[11]));
+                o1.z = pack_bf16x2(__uint_as_float(uy[12]), __uint_as_float(uy[13]));
+                o1.w = pack_bf16x2(__uint_as_float(uy[14]), __uint_as_float(uy[15]));
+                *reinterpret_cast<uint4*>(p.y + row) = o0;
+                *reinterpret_cast<uint4*>(p.y + row + 8) = o1;
+            }
+        }
+        mma_wait(c);
+        // ================= new state: S_L = (S_0 + D_0 + D_1 + D_2 + D_3) diag(exp(G_L)) =================
+        if (r < N) {
+            uint32_t v0[16], v1[16], v2[16], v3[16];
+            tmem_ld16_nowait(tm_row + C_R0 + 16 * cs, v0);
+            tmem_ld16_nowait(tm_row + C_R1 + 16 * cs, v1);
+            tmem_ld16_nowait(tm_row + C_R2 + 16 * cs, v2);
+            tmem_ld16_nowait(tm_row + C_R3 + 16 * cs, v3);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                Sck[e] = Sprev[e];
+                const float acc = ((Sprev[e] + __uint_as_float(v0[e])) + __uint_as_float(v1[e])) + __uint_as_float(v2[e]) +
+                                  __uint_as_float(v3[e]);
+                Sprev[e] = acc * sm.echk[3][16 * cs + e];
+            }
+#pragma unroll
+            for (int c4 = 0; c4 < 4; c4++) {
+                const int ch = 4 * (cs & 1) + c4;
+                *reinterpret_cast<float4*>(sm.sb + (cs >> 1) * 8192 + r * 128 + ((ch ^ (r & 7)) << 4)) =
+                    rt32(make_float4(Sprev[4 * c4], Sprev[4 * c4 + 1], Sprev[4 * c4 + 2], Sprev[4 * c4 + 3]));
+            }
+        }
+        if (tid < 4 * N) sm.eck[tid >> 6][tid & 63] = sm.echk[tid >> 6][tid & 63];
+        operands_ready();
+    }
+    write_checkpoints(nch - 1);
+    if (p.state_out && r < N) {
+        float4* dst = reinterpret_cast<float4*>(p.state_out + (((size_t)bb * H + hh) * N + r) * N + 16 * cs);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; c4++) dst[c4] = make_float4(Sprev[4 * c4], Sprev[4 * c4 + 1], Sprev[4 * c4 + 2], Sprev[4 * c4 + 3]);
     }
     tc_fence_before();
     __syncthreads();

@@ -12,6 +12,7 @@
 #include "host_util.h"
 #include "wkv7_fwd.cuh"
 #include "wkv7_bwd2.cuh"
+#include "wkv7_chunk_common.cuh"
 #include "wkv7_chunk_fwd.cuh"
 #include "wkv7_chunk_dstate.cuh"
 #include "wkv7_fwd2.cuh"

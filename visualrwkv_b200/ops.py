@@ -80,20 +80,60 @@ def adaptive_pooling(feats, out_hw):
     return f.reshape(N, D, -1).permute(0, 2, 1).contiguous()
 
 
+_pending_count = None  # (event, pinned count tensor, n_features, sample_ids) of the previous call
+
+
+def _check_pending_count():
+    global _pending_count
+    if _pending_count is None:
+        return
+    ev, host, n_feat, sample_ids = _pending_count
+    _pending_count = None
+    ev.synchronize()
+    n_sel = int(host)
+    if n_sel != n_feat:
+        warnings.warn(f"sample_id: {':::'.join(sample_ids or [])}, image tokens: {n_sel}, but image features: {n_feat}")
+    if n_sel > n_feat:
+        raise RuntimeError(f"{n_sel} image-token slots but only {n_feat} image feature rows (model.py:487-493)")
+
+
 def embed_and_scatter(emb_weight, input_ids, image_features, image_token_index, sample_ids=None):
     """preparing_embedding (model.py:481-493): emb(input_ids) with the rows where ids == 65535 replaced by the
-    image features in row-major order of appearance (bit-exact copy; gradient flows to the features)."""
+    image features in row-major order of appearance (bit-exact copy; gradient flows to the features).  Surplus
+    feature rows are dropped like the reference's `image_features[:selected.sum()]` (:487-491).
+
+    The reference reads `selected.sum()` on the host every step (a device synchronisation in the middle of the
+    forward).  Here the k-th selected row gathers feature row k on the device, and the count travels
+    to pinned host memory asynchronously: the reference's mismatch warning (and an error when there are more slots
+    than features) is raised at the next call / `flush_checks()` instead of stalling this one."""
+    global _pending_count
+    _check_pending_count()
     B, L = input_ids.shape
     D = emb_weight.shape[1]
     x = F.embedding(input_ids, emb_weight).view(B * L, D)
     sel = input_ids.view(-1) == image_token_index
-    feats = image_features.reshape(-1, D)
-    n_sel = int(sel.sum())
-    if n_sel != feats.shape[0]:
-        warnings.warn(f"sample_id: {':::'.join(sample_ids or [])}, image tokens: {n_sel}, but image features: {feats.shape[0]}")
-        feats = feats[:n_sel]
-    x = x.masked_scatter(sel.unsqueeze(-1), feats.to(x.dtype))
+    feats = image_features.reshape(-1, D).to(x.dtype)
+    rank = torch.cumsum(sel, dim=0, dtype=torch.int32) - 1          # k for the k-th selected row
+    if feats.shape[0] == 0:
+        return x.view(B, L, D)
+    gathered = feats.index_select(0, rank.clamp(0, feats.shape[0] - 1).to(torch.int64))
+    x = torch.where(sel.unsqueeze(-1), gathered, x)
+    if input_ids.is_cuda:
+        host = torch.empty((), dtype=torch.int32, pin_memory=True)
+        host.copy_(rank[-1] + 1, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        _pending_count = (ev, host, feats.shape[0], sample_ids)
+    else:
+        n_sel = int(rank[-1]) + 1
+        if n_sel != feats.shape[0]:
+            warnings.warn(f"sample_id: {':::'.join(sample_ids or [])}, image tokens: {n_sel}, but image features: {feats.shape[0]}")
     return x.view(B, L, D)
+
+
+def flush_checks():
+    """Raise / warn now for the deferred image-token count check of the last embed_and_scatter call."""
+    _check_pending_count()
 
 
 def training_loss(logits, targets, ignore_index, l2wrap):
