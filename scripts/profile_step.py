@@ -17,6 +17,10 @@ def step():
     loss = model.training_step(batch); loss.backward(); return loss
 for _ in range(3): step()
 torch.cuda.synchronize()
+import time
+for _ in range(2):
+    torch.cuda.synchronize(); t0 = time.perf_counter(); step(); t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+    print(f'CPU enqueue {1e3*(t1-t0):.1f} ms, step wall {1e3*(t2-t0):.1f} ms')
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     step(); torch.cuda.synchronize()
@@ -32,4 +36,8 @@ out = []
 for k, (n, v) in rows[:45]:
     print(f"{100*v/tot:5.1f}%  {v/1000:7.2f} ms  n={n:4d}  {k}")
     out.append({"kernel": k, "n": n, "ms": v / 1000})
+cpu = sorted([(e.self_cpu_time_total, e.key, e.count) for e in prof.key_averages()], reverse=True)[:25]
+print('--- top CPU self time (us)')
+for t, k, n in cpu:
+    print(f'{t:9.0f}  n={n:4d}  {k[:80]}')
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "profile_step.json"), "w"), indent=1)

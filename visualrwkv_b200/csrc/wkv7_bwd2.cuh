@@ -106,7 +106,7 @@ __device__ __forceinline__ void wkv7_bwd_producer_converter(Smem& sm, const CUte
 }
 
 template <int R, int NSTAGE, int UNROLL = 2>
-__global__ void __launch_bounds__((WKV_N / R) * 8 + 32)
+__global__ void __launch_bounds__((WKV_N / R) * 8 + 32)  // (capping R=4 at 192 registers for two CTAs per SM spills: slower)
 wkv7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_q,
                  const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                  const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,

@@ -216,9 +216,10 @@ extern "C" int vrwkv_wkv7_backward_ex(int B, int T, int H, const uint16_t* w, co
     cudaStream_t st = (cudaStream_t)stream;
     int var = g_bwd_variant.load();
     if (var == 0) var = ((flags | default_flags()) & VRWKV_WKV7_BOUNDED_DECAY) ? 3 : 1;
-    if (var == 3 && (T % CK_L) != 0) var = 1;
+    if ((var == 3 || var == 4) && (T % CK_L) != 0) var = 1;
     switch (var) {
         case 3: return launch_bwd_segmented<4, 3>(tm, w, q, a, b, dy, args, st);  // needs sum_chunk exp(w) < ~85
+        case 4: return launch_bwd_segmented<2, 3>(tm, w, q, a, b, dy, args, st);  // same, 2 rows per thread (8 compute warps)
         case 1: return launch_bwd2<4, 3>(tm, args, st);
         case 2: return launch_bwd2<2, 3>(tm, args, st);
         default: return vrwkv_fail(VRWKV_EINVAL, "wkv7 backward: unknown variant %d", var);
