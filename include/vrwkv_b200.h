@@ -70,8 +70,8 @@ int vrwkv_wkv7_forward_state(int B, int T, int H, const uint16_t* w, const uint1
 /* Extended entry points: `flags` may carry VRWKV_WKV7_BOUNDED_DECAY, the caller's promise that exp(w) <= 0.607
  * everywhere — true for RWKV-7's w = -softplus(.) - 0.5 (VisualRWKV-v7/v7.00/src/model.py:176), i.e. for every call
  * RWKV_Tmix_x070 makes (model.py:190).  With it (and T % 64 == 0) the library evaluates the recurrence 64 steps at a
- * time on the tensor cores: forward = chunked kernel, backward = tensor-core scan of dL/dS at chunk boundaries + the
- * step-by-step kernel on all 64-step segments concurrently.  Without it (the plain entry points above, which is what
+ * time on the tensor cores: forward = chunked kernel, backward = tensor-core scan of dL/dS at chunk boundaries + one
+ * tensor-core CTA per (batch, head, chunk) for the chunk-local gradients.  Without it (the plain entry points above, which is what
  * torch.ops.wind_backstepping binds) the step-by-step kernels run for any w.  Same tensors, same contract. */
 #define VRWKV_WKV7_BOUNDED_DECAY 1u
 int vrwkv_wkv7_forward_ex(int B, int T, int H, const uint16_t* w, const uint16_t* q,
@@ -90,7 +90,8 @@ int vrwkv_wkv7_domain_check(void);
 int vrwkv_wkv7_chunk_debug(float* buf);
 
 /* Kernel-variant selection for benchmarking (0 = default heuristic; forward 1/2 step-by-step, 3 chunked;
- * backward 1/2 step-by-step, 3 segmented). Thread-safe, process-wide. */
+ * backward 1/2 step-by-step, 3/4 dS scan + step-by-step kernel on 64-step segments, 5 dS scan + chunked tensor-core
+ * kernel). Thread-safe, process-wide. */
 int vrwkv_wkv7_set_variant(int fwd_variant, int bwd_variant);
 
 

@@ -17,7 +17,7 @@ y = torch.empty_like(v)
 s = torch.empty(B, H, T // 16, 64, 64, dtype=torch.float32, device="cuda")
 sa = torch.empty(B, T, H, 64, dtype=torch.float32, device="cuda")
 g = [torch.empty_like(w) for _ in range(6)]
-for fv, bv in ((3, 3), (3, 4)):
+for fv, bv in ((3, 3), (3, 5)):
     W.set_variant(fv, bv)
     for _ in range(3):
         torch.ops.wind_backstepping.forward(w, q, k, v, a, b, y, s, sa)

@@ -160,15 +160,22 @@ def test_error_behaviour(ops):
 # outputs stay dominated by their own rounding (1.65e-3 RMS); the fp32 side outputs (sa, s) carry the TF32 operand
 # rounding (2^-11 = 4.9e-4 per operand) — oracle/wkv7_chunked.py with tf32_round predicts 4-6e-4.
 # ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bwd_variant", [5, 3], ids=["chunked-bwd", "segmented-bwd"])
 @pytest.mark.parametrize("shape,kind,seed", [((1, 64, 1), "realistic", 3), ((2, 512, 3), "realistic", 5),
                                                ((1, 2048, 2), "realistic", 6), ((2, 256, 2), "stress", 8)])
-def test_chunked_forward_and_segmented_backward_vs_fp64_oracle(shape, kind, seed):
+def test_chunked_forward_and_tensor_core_backward_vs_fp64_oracle(shape, kind, seed, bwd_variant):
+    """bwd_variant 5 (default with bounded decay): dS scan + chunk-local tensor-core kernel; 3: dS scan + the
+    step-by-step kernel on 64-step segments."""
     from visualrwkv_b200 import wkv7 as W
     B, T, H = shape
     cpu = O.make_inputs(B, T, H, 64, seed=seed, kind=kind)
     w, q, k, v, a, b, dy = [x.cuda() for x in cpu]
     y, s, sa = W.forward_raw(w, q, k, v, a, b, bounded_decay=True)
-    g = W.backward_raw(w, q, k, v, a, b, dy, s, sa, bounded_decay=True)
+    W.set_variant(0, bwd_variant)
+    try:
+        g = W.backward_raw(w, q, k, v, a, b, dy, s, sa, bounded_decay=True)
+    finally:
+        W.set_variant(0, 0)
     W.domain_check()
     y64, s64, sa64 = O.forward(*cpu[:6])
     assert O.err_ratio(y.float().cpu().numpy(), y64) < 2.2e-3

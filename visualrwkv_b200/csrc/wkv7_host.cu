@@ -15,6 +15,7 @@
 #include "wkv7_chunk_common.cuh"
 #include "wkv7_chunk_fwd.cuh"
 #include "wkv7_chunk_dstate.cuh"
+#include "wkv7_chunk_bwd.cuh"
 #include "wkv7_fwd2.cuh"
 
 using namespace vrwkv;
@@ -132,6 +133,53 @@ static int launch_bwd_segmented(const CUtensorMap* tm, const void* w, const void
     return VRWKV_OK;
 }
 
+static int ensure_pool_keeps_memory() {
+    // stream-ordered workspaces: keep freed blocks in the device's pool instead of returning them to the OS at every
+    // synchronisation (the default release threshold of 0 makes each step pay a real cudaMalloc)
+    static std::atomic<unsigned> pool_ready{0};
+    int dev = 0;
+    VRWKV_CUDA(cudaGetDevice(&dev));
+    if (!(pool_ready.load() & (1u << dev))) {
+        cudaMemPool_t pool;
+        VRWKV_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t keep = UINT64_MAX;
+        VRWKV_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        pool_ready.fetch_or(1u << dev);
+    }
+    return VRWKV_OK;
+}
+
+// backward entirely on the tensor cores: dS boundary scan, then one CTA per (batch, head, chunk)
+static int launch_bwd_chunked(const uint16_t* w, const uint16_t* q, const uint16_t* k, const uint16_t* v, const uint16_t* a,
+                              const uint16_t* b, const uint16_t* dy, const float* sa, const Wkv7BwdArgs& args, cudaStream_t st) {
+    const int B = args.B, T = args.T, H = args.H, nch = T / CK_L;
+    int rc = ensure_pool_keeps_memory();
+    if (rc) return rc;
+    const size_t nstate = (size_t)B * H * nch * WKV_N * WKV_N;
+    float* ws = nullptr;  // [ds | gws]
+    VRWKV_CUDA(cudaMallocAsync((void**)&ws, 2 * nstate * sizeof(float), st));
+    CUtensorMap cm[7];
+    const void* in[7] = {w, q, k, v, a, b, dy};
+    for (int i = 0; i < 7; i++)
+        if ((rc = make_chunk_map(&cm[i], in[i], B, T, H))) return rc;
+    if (nch > 1) {
+        const size_t smem = sizeof(Wkv7DstateSmem) + 1024;
+        VRWKV_CUDA(cudaFuncSetAttribute(wkv7_chunk_dstate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        Wkv7DstateArgs da{B, T, H, ws};
+        wkv7_chunk_dstate_kernel<<<dim3(H, B), CK_THREADS, smem, st>>>(cm[0], cm[1], cm[4], cm[5], cm[6], da);
+        VRWKV_CUDA(cudaGetLastError());
+        vrwkv_count_launch(1);
+    }
+    const size_t smem = sizeof(Wkv7ChunkBwdSmem) + 1024;
+    VRWKV_CUDA(cudaFuncSetAttribute(wkv7_chunk_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    Wkv7ChunkBwdArgs ca{B, T, H, w, q, k, v, a, b, dy, sa, args.s, ws, ws + nstate, args.dw, args.dq, args.dk, args.dv, args.da, args.db};
+    wkv7_chunk_bwd_kernel<<<dim3(H, B, nch), CK_THREADS, smem, st>>>(cm[0], cm[1], cm[2], cm[3], cm[4], cm[5], cm[6], ca);
+    VRWKV_CUDA(cudaGetLastError());
+    vrwkv_count_launch(1);
+    VRWKV_CUDA(cudaFreeAsync(ws, st));
+    return VRWKV_OK;
+}
+
 static int check_common(int B, int T, int H, const void* const* ptrs, int nptr) {
     if (B <= 0 || T <= 0 || H <= 0) return vrwkv_fail(VRWKV_EINVAL, "wkv7: B,T,H must be positive (got %d,%d,%d)", B, T, H);
     if ((long long)B * T >= (1ll << 31)) return vrwkv_fail(VRWKV_EUNSUP, "wkv7: B*T too large");
@@ -215,9 +263,10 @@ extern "C" int vrwkv_wkv7_backward_ex(int B, int T, int H, const uint16_t* w, co
     Wkv7BwdArgs args{B, T, H, s, dw, dq, dk, dv, da, db};
     cudaStream_t st = (cudaStream_t)stream;
     int var = g_bwd_variant.load();
-    if (var == 0) var = ((flags | default_flags()) & VRWKV_WKV7_BOUNDED_DECAY) ? 3 : 1;
-    if ((var == 3 || var == 4) && (T % CK_L) != 0) var = 1;
+    if (var == 0) var = ((flags | default_flags()) & VRWKV_WKV7_BOUNDED_DECAY) ? 5 : 1;
+    if ((var == 3 || var == 4 || var == 5) && (T % CK_L) != 0) var = 1;
     switch (var) {
+        case 5: return launch_bwd_chunked(w, q, k, v, a, b, dy, sa, args, st);  // tensor cores only (bounded decay)
         case 3: return launch_bwd_segmented<4, 3>(tm, w, q, a, b, dy, args, st);  // needs sum_chunk exp(w) < ~85
         case 4: return launch_bwd_segmented<2, 3>(tm, w, q, a, b, dy, args, st);  // same, 2 rows per thread (8 compute warps)
         case 1: return launch_bwd2<4, 3>(tm, args, st);
