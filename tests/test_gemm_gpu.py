@@ -9,8 +9,8 @@ pytestmark = pytest.mark.gpu
 
 def _ref(a, w, epi, res):
     c = a.float() @ w.float().t()
-    if epi == 1:
-        c = torch.relu(c) ** 2
+    if epi == 1:  # relu(key(x))**2 in bf16 eager: the Linear output is rounded to bf16 before the square (model.py:225)
+        c = torch.relu(c.to(torch.bfloat16).float()) ** 2
     if epi == 2:
         c = c + res.float()
     return c
@@ -30,7 +30,8 @@ def test_gemm_matches_fp32_reference(M, N, K, epi):
     ref = _ref(a, w, epi, res)
     # one bf16 rounding of an fp32-accumulated result: |err| <= 2^-8 |ref| (+ a little for accumulation order)
     err = (c.float() - ref).abs()
-    assert float((err - (2.0 ** -8) * ref.abs()).max()) <= 2e-3
+    # (relu^2: a pre-activation that sits on a bf16 rounding boundary may round the other way -> one more ulp, squared)
+    assert float((err - (2.0 ** -8) * ref.abs() * (3.0 if epi == 1 else 1.0)).max()) <= 2e-3
     assert float(err.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt().clamp_min(1e-12)) < 2.5e-3
 
 
