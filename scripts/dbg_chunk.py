@@ -31,3 +31,18 @@ torch.cuda.synchronize()
 ts = [int(x) for x in dbg.cpu().numpy()[2048:2048 + 40]]
 print("no-ckpt deltas:", [ts[i + 1] - ts[i] for i in range(len(ts) - 1) if ts[i + 1] > 0])
 _lib.check(_lib.lib().vrwkv_wkv7_chunk_debug(ctypes.c_void_p(0)), "dbg")
+
+# ---- chunked backward: clock stamps of CTA (0,0,chunk 1) ----
+_lib.check(_lib.lib().vrwkv_wkv7_chunk_debug(ctypes.c_void_p(dbg.data_ptr())), "dbg")
+dbg.zero_()
+cpu = list(O.make_inputs(1, T, 1, 64, seed=3))
+w, q, k, v, a, b, dy = [x.cuda() for x in cpu]
+W.set_variant(3, 5)
+torch.ops.wind_backstepping.forward(w, q, k, v, a, b, y, s, sa)
+g = [torch.empty_like(w) for _ in range(6)]
+torch.ops.wind_backstepping.backward(w, q, k, v, a, b, dy, s, sa, *g)
+torch.cuda.synchronize()
+ts = [int(x) for x in dbg.cpu().numpy()[3072:3072 + 48]]
+print("bwd stamps:", ts)
+print("bwd deltas:", [ts[i + 1] - ts[i] for i in range(len(ts) - 1) if ts[i + 1] > 0])
+_lib.check(_lib.lib().vrwkv_wkv7_chunk_debug(ctypes.c_void_p(0)), "dbg")

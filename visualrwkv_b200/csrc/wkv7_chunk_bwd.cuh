@@ -30,17 +30,17 @@ struct Wkv7ChunkBwdArgs {
 struct alignas(1024) Wkv7ChunkBwdSmem {
     uint8_t aq[32768];   // [At;Qt]: K-major for the scores, re-swizzled in place to MN-major for dA^T [At;Qt]
     uint8_t bk[32768];   // [Bt;Kt]: K-major for the scores and [Bt;Kt] dZ^T, then MN-major for dA [Bt;Kt]
-    uint8_t dz[16384];   // dZ [i][j]: K-major for [Bt;Kt] dZ^T, then MN-major for [U;V] dZ
+    uint8_t dz[16384];   // dZ [i][j]: K-major for [Bt;Kt] dZ^T, then MN-major for [U;V] dZ; then (with x16) dA (q rows) MN
     uint8_t x16[16384];  // dY (MN) -> dU (MN) -> dR (MN)
-    uint8_t sa_[32768];  // a-row scores [t][A_ab | A_ak], MN-major (M = column)
-    uint8_t z1[32768];   // TMA tiles 0-3 | q-row scores [t][A_qb | A_qk] MN | [dR;dY] K-major | dA half K-major | epilogue
-    uint8_t z2[32768];   // TMA tiles 4-6 | A_ab fp32 (16 KB) + Tinv MN (16 KB) | [U;V] K-major | dA half MN | epilogue
+    uint8_t sa_[32768];  // a-row scores [t][A_ab | A_ak], MN-major (M = column); then dA (q rows) K-major
+    uint8_t z1[32768];   // TMA tiles 0-3 | q-row scores [t][A_qb | A_qk] MN | [dR;dY] K-major | dA (a rows) K-major | epilogue
+    uint8_t z2[32768];   // TMA tiles 4-6 | A_ab fp32 (16 KB) + Tinv MN (16 KB) | [U;V] K-major | dA (a rows) MN | epilogue
     uint8_t s0[16384];   // S_0 as stored by the forward ([j][i]) = K-major B operand of [dR;dY] S_0; Tinv's M=128 tail
     float esc[32 * 32];
     float part[8][WKV_N];
     float el[WKV_N];
     float gl[WKV_N];
-    uint64_t bar_in, bar_mma;
+    uint64_t bar_in, bar_mma;  // bar_mma: one arrival per issuing warp (warps 0-3)
     uint32_t tmem_base;
 };
 
@@ -55,11 +55,9 @@ wkv7_chunk_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
     uint8_t* const tiles = sm.z1;         // 7 x 8 KB (runs on into z2)
     uint8_t* const sq = sm.z1;            // q-row scores MN: 4 column blocks x 64 k-lines
     uint8_t* const ry = sm.z1;            // [dR;dY] K-major: 2 k-atoms x 128 rows
-    uint8_t* const dak = sm.z1;           // dA half, K-major: 4 k-atoms x 64 rows
     uint8_t* const aab = sm.z2;           // A_ab fp32
     uint8_t* const tinv = sm.z2 + 16384;  // Tinv MN: 2 column blocks x 64 k-lines (M = 128 reads on into s0)
     uint8_t* const uv = sm.z2;            // [U;V] K-major: 2 k-atoms x 128 rows
-    uint8_t* const dam = sm.z2;           // dA half, MN-major: 4 column blocks x 64 k-lines
 
     const int hh = blockIdx.x, bb = blockIdx.y, c = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -74,7 +72,7 @@ wkv7_chunk_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
 
     if (tid == 0) {
         mbar_init(&sm.bar_in, 1);
-        mbar_init(&sm.bar_mma, 1);
+        mbar_init(&sm.bar_mma, 4);
         fence_mbar_init();
     }
     __syncwarp();
@@ -99,23 +97,44 @@ wkv7_chunk_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
     }
     __syncwarp();
 
+    float* const dbg = (hh == 0 && bb == 0 && c == 1) ? g_chunk_dbg : nullptr;
+    const long long tstamp0 = clock64();
+    int tsi = 0;
+    auto stamp = [&]() {
+        if (dbg && tid == 0) dbg[3072 + tsi++] = (float)(clock64() - tstamp0);
+    };
+    {   // the delta phase reads U (= sa rows) and S_0 from global memory: start pulling them into L2 now
+        const int t = tid >> 3, i0 = 8 * (tid & 7);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.sa + row0 + (size_t)t * rstride + i0));
+        if (c > 0)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.s + ((((size_t)bb * H + hh) * (T / WKV_TC) + (size_t)c * 4 - 1) * N + t) * N + i0));
+    }
     uint32_t mph = 0;
     auto mma_wait = [&]() {
+        stamp();
         mbar_wait(&sm.bar_mma, mph & 1);
         mph++;
         tc_fence_after();
         __syncwarp();
+        stamp();
     };
     auto operands_ready = [&]() {
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
     };
+    const uint32_t b4 = smem_u32(&sm) >> 4;
+    const uint32_t O_AQ = (uint32_t)(sm.aq - (uint8_t*)&sm), O_BK = (uint32_t)(sm.bk - (uint8_t*)&sm), O_DZ = (uint32_t)(sm.dz - (uint8_t*)&sm),
+                   O_X16 = (uint32_t)(sm.x16 - (uint8_t*)&sm), O_SA = (uint32_t)(sm.sa_ - (uint8_t*)&sm), O_Z1 = (uint32_t)(sm.z1 - (uint8_t*)&sm),
+                   O_Z2 = (uint32_t)(sm.z2 - (uint8_t*)&sm), O_S0 = (uint32_t)(sm.s0 - (uint8_t*)&sm);
+    const bool issuer = lane == 0 && warp < 4;  // the four threads that issue tensor-core work (independent accumulators)
     constexpr uint32_t ID_KK_128 = umma_idesc_tf32(128, 128), ID_KK = umma_idesc_tf32(128, 64), ID_KM = umma_idesc_tf32(128, 64, 0, 1),
                        ID_MM = umma_idesc_tf32(128, 64, 1, 1);
     auto f4 = [](const uint32_t* v) { return make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])); };
 
+    stamp();
     mbar_wait(&sm.bar_in, 0);
+    stamp();
     // ================= P1: decay prefix sums, scaled operands, dY operand, G to the workspace =================
     {
         const int hf = warp & 1, rg = warp >> 1;
@@ -176,19 +195,18 @@ wkv7_chunk_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
     }
     operands_ready();
     // ================= alpha: scores = [At;Qt][Bt;Kt]^T ; ACC1 = [Bt;Kt] dZ^T =================
-    if (tid == 0) {
+    if (issuer) {
         tc_fence_after();
+        if (warp == 0) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const uint64_t da = umma_desc_advance(umma_desc_sw128(sm.aq + (k >> 2) * 16384), (k & 3) * 32);
-            const uint64_t db = umma_desc_advance(umma_desc_sw128(sm.bk + (k >> 2) * 16384), (k & 3) * 32);
-            umma_tf32(tmem + C_SC, da, db, ID_KK_128, k > 0);
-        }
+            for (int k = 0; k < 8; k++)
+                umma_tf32(tmem + C_SC, desc_km(b4, O_AQ + (k >> 2) * 16384 + (k & 3) * 32), desc_km(b4, O_BK + (k >> 2) * 16384 + (k & 3) * 32),
+                          ID_KK_128, k > 0);
+        } else if (warp == 1) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const uint64_t da = umma_desc_advance(umma_desc_sw128(sm.bk + (k >> 2) * 16384), (k & 3) * 32);
-            const uint64_t db = umma_desc_advance(umma_desc_sw128(sm.dz + (k >> 2) * 8192), (k & 3) * 32);
-            umma_tf32(tmem + C_ACC1, da, db, ID_KK, k > 0);
+            for (int k = 0; k < 8; k++)
+                umma_tf32(tmem + C_ACC1, desc_km(b4, O_BK + (k >> 2) * 16384 + (k & 3) * 32), desc_km(b4, O_DZ + (k >> 2) * 8192 + (k & 3) * 32),
+                          ID_KK, k > 0);
         }
         umma_commit(&sm.bar_mma);
     }
@@ -250,13 +268,16 @@ wkv7_chunk_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
     }
     operands_ready();
     // ================= beta: ACC1 += [A_qb|A_qk]^T dY   (inverse meanwhile) =================
-    if (tid == 0) {
+    if (issuer) {
         tc_fence_after();
-        const uint64_t da = umma_desc_mn_tf32(sq, 8192, 512), db = umma_desc_mn_tf32(sm.x16, 8192, 512);
+        if (warp == 0) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) umma_tf32(tmem + C_ACC1, umma_desc_advance(da, k * 1024), umma_desc_advance(db, k * 1024), ID_MM, 1);
+            for (int k = 0; k < 8; k++)
+                umma_tf32(tmem + C_ACC1, desc_mn(b4, O_Z1 + k * 1024, 8192), desc_mn(b4, O_X16 + k * 1024, 8192), ID_MM, 1);
+        }
         umma_commit(&sm.bar_mma);
     }
+    stamp();
     chunk_tri_inverse(aab, sm.esc, tid, [&](int t, int s) { return tinv + (s >> 5) * 8192 + sw32_off(t, s & 31); });
     mma_wait();
     if (r < 64) {  // dU -> operand
@@ -268,12 +289,26 @@ wkv7_chunk_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
     }
     operands_ready();
     // ================= gamma: dR = Tinv^T dU =================
-    if (tid == 0) {
+    if (issuer) {
         tc_fence_after();
-        const uint64_t da = umma_desc_mn_tf32(tinv, 8192, 512), db = umma_desc_mn_tf32(sm.x16, 8192, 512);
+        if (warp == 0) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) umma_tf32(tmem + C_R, umma_desc_advance(da, k * 1024), umma_desc_advance(db, k * 1024), ID_MM, k > 0);
+            for (int k = 0; k < 8; k++)
+                umma_tf32(tmem + C_R, desc_mn(b4, O_Z2 + 16384 + k * 1024, 8192), desc_mn(b4, O_X16 + k * 1024, 8192), ID_MM, k > 0);
+        }
         umma_commit(&sm.bar_mma);
+    }
+    // operands of the delta phase that come from global memory: issue the loads now, behind the gamma product
+    const int dt = tid >> 3, di0 = 8 * (tid & 7);
+    const uint4 g_dy = __ldg(reinterpret_cast<const uint4*>(p.dy + row0 + (size_t)dt * rstride + di0));
+    const uint4 g_v = __ldg(reinterpret_cast<const uint4*>(p.v + row0 + (size_t)dt * rstride + di0));
+    const float4 g_u0 = __ldg(reinterpret_cast<const float4*>(p.sa + row0 + (size_t)dt * rstride + di0));
+    const float4 g_u1 = __ldg(reinterpret_cast<const float4*>(p.sa + row0 + (size_t)dt * rstride + di0) + 1);
+    float4 g_s0 = make_float4(0.f, 0.f, 0.f, 0.f), g_s1 = g_s0;
+    if (c > 0) {  // S_0: checkpoint memory [j][i] holds S_ij (wkv7_cuda.cu:44-50) = K-major (N = j, K = i)
+        const float4* ss = reinterpret_cast<const float4*>(p.s + ((((size_t)bb * H + hh) * (T / WKV_TC) + (size_t)c * 4 - 1) * N + dt) * N + di0);
+        g_s0 = __ldg(ss);
+        g_s1 = __ldg(ss + 1);
     }
     mma_wait();
     // ================= delta operands: [dR;dY] (K-major), dR (MN), [U;V] (K-major), S_0 =================
@@ -289,118 +324,146 @@ wkv7_chunk_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
         }
     }
     {
-        const int t = tid >> 3, i0 = 8 * (tid & 7);
+        const int t = dt, i0 = di0;
         const int ch = (i0 & 31) >> 2, at = i0 >> 5;
         auto put8 = [&](uint8_t* base, int row, float4 lo, float4 hi) {
             *reinterpret_cast<float4*>(base + at * 16384 + row * 128 + ((ch ^ (row & 7)) << 4)) = lo;
             *reinterpret_cast<float4*>(base + at * 16384 + row * 128 + (((ch + 1) ^ (row & 7)) << 4)) = hi;
         };
-        auto bf8 = [&](const uint16_t* ptr, float4& lo, float4& hi) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(ptr));
+        auto bf8 = [&](const uint4 u, float4& lo, float4& hi) {
             lo = make_float4(bf16lo_to_f32(u.x), bf16hi_to_f32(u.x), bf16lo_to_f32(u.y), bf16hi_to_f32(u.y));
             hi = make_float4(bf16lo_to_f32(u.z), bf16hi_to_f32(u.z), bf16lo_to_f32(u.w), bf16hi_to_f32(u.w));
         };
         float4 lo, hi;
-        bf8(p.dy + row0 + (size_t)t * rstride + i0, lo, hi);
+        bf8(g_dy, lo, hi);
         put8(ry, 64 + t, lo, hi);
-        bf8(p.v + row0 + (size_t)t * rstride + i0, lo, hi);
+        bf8(g_v, lo, hi);
         put8(uv, 64 + t, lo, hi);
-        const float4* us = reinterpret_cast<const float4*>(p.sa + row0 + (size_t)t * rstride + i0);
-        put8(uv, t, rt32(__ldg(us)), rt32(__ldg(us + 1)));
-        // S_0: checkpoint memory [j][i] holds S_ij (wkv7_cuda.cu:44-50) = K-major (N = j, K = i)
-        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
-        if (c > 0) {
-            const float4* ss = reinterpret_cast<const float4*>(p.s + ((((size_t)bb * H + hh) * (T / WKV_TC) + (size_t)c * 4 - 1) * N + t) * N + i0);
-            s0 = rt32(__ldg(ss));
-            s1 = rt32(__ldg(ss + 1));
-        }
-        *reinterpret_cast<float4*>(sm.s0 + at * 8192 + t * 128 + ((ch ^ (t & 7)) << 4)) = s0;
-        *reinterpret_cast<float4*>(sm.s0 + at * 8192 + t * 128 + (((ch + 1) ^ (t & 7)) << 4)) = s1;
+        put8(uv, t, rt32(g_u0), rt32(g_u1));
+        *reinterpret_cast<float4*>(sm.s0 + at * 8192 + t * 128 + ((ch ^ (t & 7)) << 4)) = rt32(g_s0);
+        *reinterpret_cast<float4*>(sm.s0 + at * 8192 + t * 128 + (((ch + 1) ^ (t & 7)) << 4)) = rt32(g_s1);
     }
     operands_ready();
     // ================= delta: dA = [dR;dY][U;V]^T ; dAt1 / dQt1 = [dR;dY] S_0 ; [dBt1;dKt1] = [U;V] dZ ; dV += A_ak^T dR =====
-    if (tid == 0) {
+    if (issuer) {
         tc_fence_after();
+        if (warp == 0) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const uint64_t da = umma_desc_advance(umma_desc_sw128(ry + (k >> 2) * 16384), (k & 3) * 32);
-            const uint64_t db = umma_desc_advance(umma_desc_sw128(uv + (k >> 2) * 16384), (k & 3) * 32);
-            umma_tf32(tmem + C_DA, da, db, ID_KK_128, k > 0);
+            for (int k = 0; k < 8; k++)
+                umma_tf32(tmem + C_DA, desc_km(b4, O_Z1 + (k >> 2) * 16384 + (k & 3) * 32), desc_km(b4, O_Z2 + (k >> 2) * 16384 + (k & 3) * 32),
+                          ID_KK_128, k > 0);
+        } else if (warp == 1) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint64_t db = desc_km(b4, O_S0 + (k >> 2) * 8192 + (k & 3) * 32);
+                umma_tf32(tmem + C_A, desc_km(b4, O_Z1 + (k >> 2) * 16384 + (k & 3) * 32), db, ID_KK, k > 0);
+                umma_tf32(tmem + C_Q, desc_km(b4, O_Z1 + 64 * 128 + (k >> 2) * 16384 + (k & 3) * 32), db, ID_KK, k > 0);
+            }
+        } else if (warp == 2) {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                umma_tf32(tmem + C_BK, desc_km(b4, O_Z2 + (k >> 2) * 16384 + (k & 3) * 32), desc_mn(b4, O_DZ + k * 1024, 8192), ID_KM, k > 0);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                umma_tf32(tmem + C_ACC1, desc_mn(b4, O_SA + k * 1024, 8192), desc_mn(b4, O_X16 + k * 1024, 8192), ID_MM, 1);
         }
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const uint64_t da = umma_desc_advance(umma_desc_sw128(ry + (k >> 2) * 16384), (k & 3) * 32);
-            const uint64_t db = umma_desc_advance(umma_desc_sw128(sm.s0 + (k >> 2) * 8192), (k & 3) * 32);
-            umma_tf32(tmem + C_A, da, db, ID_KK, k > 0);
-            umma_tf32(tmem + C_Q, umma_desc_advance(da, 64 * 128), db, ID_KK, k > 0);
-        }
-        const uint64_t dzm = umma_desc_mn_tf32(sm.dz, 8192, 512);
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const uint64_t da = umma_desc_advance(umma_desc_sw128(uv + (k >> 2) * 16384), (k & 3) * 32);
-            umma_tf32(tmem + C_BK, da, umma_desc_advance(dzm, k * 1024), ID_KM, k > 0);
-        }
-        const uint64_t sam = umma_desc_mn_tf32(sm.sa_, 8192, 512), drm = umma_desc_mn_tf32(sm.x16, 8192, 512);
-#pragma unroll
-        for (int k = 0; k < 8; k++) umma_tf32(tmem + C_ACC1, umma_desc_advance(sam, k * 1024), umma_desc_advance(drm, k * 1024), ID_MM, 1);
         umma_commit(&sm.bar_mma);
     }
     mma_wait();
-    // ================= epsilon: the two halves of dA (a rows, then q rows) through the same operand buffers =================
-#pragma unroll 1
-    for (int half = 0; half < 2; half++) {
-        if ((r >= 64) == (half == 1)) {
-            uint32_t v[32];
-            tmem_ld32(tm_row + C_DA + 32 * cs, v);
-            const int t = r & 63;
-            float o[32];
-#pragma unroll
-            for (int e = 0; e < 32; e++) {
-                const int s = 32 * (cs & 1) + e;
-                const bool keep = half ? (s <= t) : (s < t);
-                o[e] = keep ? rt32(__uint_as_float(v[e])) : 0.f;
-            }
-#pragma unroll
-            for (int c4 = 0; c4 < 8; c4++) {
-                const float4 x = make_float4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
-                *reinterpret_cast<float4*>(dak + cs * 8192 + t * 128 + ((c4 ^ (t & 7)) << 4)) = x;
-                *reinterpret_cast<float4*>(dam + cs * 8192 + sw32_off(t, 4 * c4)) = x;
-            }
-        }
-        operands_ready();
-        if (tid == 0) {
-            tc_fence_after();
-            const uint64_t bkm = umma_desc_mn_tf32(sm.bk, 16384, 512);
-#pragma unroll
-            for (int k = 0; k < 16; k++) {
-                const uint64_t da = umma_desc_advance(umma_desc_sw128(dak + (k >> 2) * 8192), (k & 3) * 32);
-                umma_tf32(tmem + (half ? C_Q : C_A), da, umma_desc_advance(bkm, k * 1024), ID_KM, 1);
-            }
-            const uint64_t dmm = umma_desc_mn_tf32(dam, 8192, 512);
-            const uint64_t aqm = umma_desc_mn_tf32(sm.aq + (half ? 64 * 128 : 0), 16384, 512);
-#pragma unroll
-            for (int k = 0; k < 8; k++) umma_tf32(tmem + C_BK, umma_desc_advance(dmm, k * 1024), umma_desc_advance(aqm, k * 1024), ID_MM, 1);
-            umma_commit(&sm.bar_mma);
-        }
-        mma_wait();
-    }
-    // ================= epilogue =================
-    float* const kk_s = reinterpret_cast<float*>(sm.z1);          // (dk k)[t][j]
-    float* const p1_s = reinterpret_cast<float*>(sm.z1 + 16384);  // (dq q - db b)[t][j]
-    float* const p2_s = reinterpret_cast<float*>(sm.z2);          // (da a)[t][j]
+    // ================= epsilon: masked dA as operands (a rows -> z1 / z2, q rows -> sa_ / dz+x16), then both products =========
     {
-        const int t = r & 63, j0 = 16 * cs;
-        const size_t go = row0 + (size_t)t * rstride + j0;
-        const float* grow = p.gws + chunk_id * (L * N) + t * N + j0;
-        float G[16];
+        uint32_t v[32];
+        stamp();
+        tmem_ld32(tm_row + C_DA + 32 * cs, v);
+        stamp();
+        const int t = r & 63;
+        const bool qrow = r >= 64;
+        uint8_t* const kdst = (qrow ? sm.sa_ : sm.z1) + cs * 8192 + t * 128;  // K-major: 4 k-atoms x 64 rows
+        uint8_t* const mdst = (qrow ? sm.dz : sm.z2) + cs * 8192;              // MN-major: 4 column blocks x 64 k-lines
+#pragma unroll
+        for (int c4 = 0; c4 < 8; c4++) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int s_ = 32 * (cs & 1) + 4 * c4 + e;
+                const bool keep = qrow ? (s_ <= t) : (s_ < t);
+                o[e] = keep ? rt32(__uint_as_float(v[4 * c4 + e])) : 0.f;
+            }
+            const float4 x = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(kdst + ((c4 ^ (t & 7)) << 4)) = x;
+            *reinterpret_cast<float4*>(mdst + sw32_off(t, 4 * c4)) = x;
+        }
+    }
+    stamp();
+    fence_proxy_async();
+    stamp();
+    tc_fence_before();
+    __syncthreads();
+    stamp();
+    if (issuer) {
+        tc_fence_after();
+        if (warp == 0) {  // dAt += dA_a [Bt;Kt]      (one accumulator is fed by one issuing thread only)
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                umma_tf32(tmem + C_A, desc_km(b4, O_Z1 + (k >> 2) * 8192 + (k & 3) * 32), desc_mn(b4, O_BK + k * 1024, 16384), ID_KM, 1);
+        } else if (warp == 1) {  // dQt += dA_q [Bt;Kt]
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                umma_tf32(tmem + C_Q, desc_km(b4, O_SA + (k >> 2) * 8192 + (k & 3) * 32), desc_mn(b4, O_BK + k * 1024, 16384), ID_KM, 1);
+        } else if (warp == 2) {  // [dBt;dKt] += dA_a^T At + dA_q^T Qt
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                umma_tf32(tmem + C_BK, desc_mn(b4, O_Z2 + k * 1024, 8192), desc_mn(b4, O_AQ + k * 1024, 16384), ID_MM, 1);
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                umma_tf32(tmem + C_BK, desc_mn(b4, O_DZ + k * 1024, 8192), desc_mn(b4, O_AQ + 64 * 128 + k * 1024, 16384), ID_MM, 1);
+        }
+        umma_commit(&sm.bar_mma);
+    }
+    stamp();
+    // inputs of the element-wise epilogue: loads issued now, consumed after the products above have finished
+    const int et = r & 63, ej0 = 16 * cs;
+    const size_t ego = row0 + (size_t)et * rstride + ej0;
+    const float* egrow = p.gws + chunk_id * (L * N) + et * N + ej0;
+    float4 eG[4], eGm[4];
+    uint4 ein[3][2];
+#pragma unroll
+    for (int c4 = 0; c4 < 4; c4++) {
+        eG[c4] = *reinterpret_cast<const float4*>(egrow + 4 * c4);
+        eGm[c4] = (r < 64 && et > 0) ? *reinterpret_cast<const float4*>(egrow - N + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    {
+        const uint16_t* src0 = (r >= 64) ? p.k : p.a;
+        ein[0][0] = __ldg(reinterpret_cast<const uint4*>(src0 + ego));
+        ein[0][1] = __ldg(reinterpret_cast<const uint4*>(src0 + ego) + 1);
+        if (r < 64) {
+            ein[1][0] = __ldg(reinterpret_cast<const uint4*>(p.q + ego));
+            ein[1][1] = __ldg(reinterpret_cast<const uint4*>(p.q + ego) + 1);
+            ein[2][0] = __ldg(reinterpret_cast<const uint4*>(p.b + ego));
+            ein[2][1] = __ldg(reinterpret_cast<const uint4*>(p.b + ego) + 1);
+        }
+    }
+    mma_wait();
+    // ================= epilogue =================
+    stamp();
+    // three [64][64] fp32 scratch arrays with a row pitch of 65 floats: written row-wise by lanes that differ in t
+    // (pitch 64 would put a whole warp on one bank), read column-wise by lanes that differ in j
+    constexpr int EP = 65;
+    float* const kk_s = reinterpret_cast<float*>(sm.z1);              // (dk k)[t][j]
+    float* const p1_s = reinterpret_cast<float*>(sm.z1) + 64 * EP;    // (dq q - db b)[t][j]
+    float* const p2_s = reinterpret_cast<float*>(sm.z1) + 128 * EP;   // (da a)[t][j]   (runs on into z2)
+    {
+        const int t = et, j0 = ej0;
+        const size_t go = ego;
+        float G[16], Gm[16];
 #pragma unroll
         for (int c4 = 0; c4 < 4; c4++) {
-            const float4 x = *reinterpret_cast<const float4*>(grow + 4 * c4);
-            G[4 * c4] = x.x; G[4 * c4 + 1] = x.y; G[4 * c4 + 2] = x.z; G[4 * c4 + 3] = x.w;
+            G[4 * c4] = eG[c4].x; G[4 * c4 + 1] = eG[c4].y; G[4 * c4 + 2] = eG[c4].z; G[4 * c4 + 3] = eG[c4].w;
+            Gm[4 * c4] = eGm[c4].x; Gm[4 * c4 + 1] = eGm[c4].y; Gm[4 * c4 + 2] = eGm[c4].z; Gm[4 * c4 + 3] = eGm[c4].w;
         }
-        auto ld16 = [&](const uint16_t* ptr, float (&o)[16]) {
-            const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(ptr)), u1 = __ldg(reinterpret_cast<const uint4*>(ptr) + 1);
-            const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+        auto un16 = [&](const uint4 (&u)[2], float (&o)[16]) {
+            const uint32_t w[8] = {u[0].x, u[0].y, u[0].z, u[0].w, u[1].x, u[1].y, u[1].z, u[1].w};
 #pragma unroll
             for (int e = 0; e < 8; e++) {
                 o[2 * e] = bf16lo_to_f32(w[e]);
@@ -420,12 +483,12 @@ wkv7_chunk_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
             tmem_ld16_nowait(tm_row + C_ACC1 + j0, vv);
             tmem_ld_wait();
             float kin[16], dk[16], dv[16];
-            ld16(p.k + go, kin);
+            un16(ein[0], kin);
 #pragma unroll
             for (int e = 0; e < 16; e++) {
                 dk[e] = __uint_as_float(vk[e]) * __expf(-G[e]);
                 dv[e] = __uint_as_float(vv[e]);
-                kk_s[t * N + j0 + e] = dk[e] * kin[e];
+                kk_s[t * EP + j0 + e] = dk[e] * kin[e];
             }
             st16(p.dk + go, dk);
             st16(p.dv + go, dv);
@@ -435,34 +498,24 @@ wkv7_chunk_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
             tmem_ld16_nowait(tm_row + C_Q + j0, vq);
             tmem_ld16_nowait(tm_row + C_BK + j0, vb);
             tmem_ld_wait();
-            float Gm[16];
-            if (t > 0) {
-#pragma unroll
-                for (int c4 = 0; c4 < 4; c4++) {
-                    const float4 x = *reinterpret_cast<const float4*>(grow - N + 4 * c4);
-                    Gm[4 * c4] = x.x; Gm[4 * c4 + 1] = x.y; Gm[4 * c4 + 2] = x.z; Gm[4 * c4 + 3] = x.w;
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 16; e++) Gm[e] = 0.f;
-            }
             float ain[16], qin[16], bin[16], da[16], dq[16], db[16];
-            ld16(p.a + go, ain);
-            ld16(p.q + go, qin);
-            ld16(p.b + go, bin);
+            un16(ein[0], ain);
+            un16(ein[1], qin);
+            un16(ein[2], bin);
 #pragma unroll
             for (int e = 0; e < 16; e++) {
                 da[e] = __uint_as_float(va[e]) * __expf(Gm[e]);
                 dq[e] = __uint_as_float(vq[e]) * __expf(G[e]);
                 db[e] = __uint_as_float(vb[e]) * __expf(-G[e]);
-                p1_s[t * N + j0 + e] = dq[e] * qin[e] - db[e] * bin[e];
-                p2_s[t * N + j0 + e] = da[e] * ain[e];
+                p1_s[t * EP + j0 + e] = dq[e] * qin[e] - db[e] * bin[e];
+                p2_s[t * EP + j0 + e] = da[e] * ain[e];
             }
             st16(p.da + go, da);
             st16(p.dq + go, dq);
             st16(p.db + go, db);
         }
     }
+    stamp();
     // d/dG_L through S_L = Z diag(e^{G_L}): sum_i dS_L[i][j] S_L[i][j]   (S_L: checkpoint after step 63 of this chunk)
     {
         const int j = tid & 63, ig = tid >> 6;
@@ -485,6 +538,7 @@ wkv7_chunk_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
         sm.gl[tid] = x;
     }
     __syncthreads();
+    stamp();
     // dG_t = p1_t - kk_t + p2_{t+1} (+ gl at t = 63); dg = suffix sum over t; dw = dg * (-e^w)
     {
         const int j = tid & 63, rg = tid >> 6;
@@ -493,8 +547,8 @@ wkv7_chunk_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
 #pragma unroll
         for (int k = 7; k >= 0; k--) {
             const int t = 8 * rg + k;
-            const float nxt = (t == L - 1) ? sm.gl[j] : p2_s[(t + 1) * N + j];
-            run += p1_s[t * N + j] - kk_s[t * N + j] + nxt;
+            const float nxt = (t == L - 1) ? sm.gl[j] : p2_s[(t + 1) * EP + j];
+            run += p1_s[t * EP + j] - kk_s[t * EP + j] + nxt;
             dG[k] = run;  // suffix sum inside the row group
         }
         __syncthreads();  // everyone has read gl / part before part is reused
@@ -511,6 +565,7 @@ wkv7_chunk_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
             p.dw[go] = f32_to_bf16_bits((dG[k] + off) * g);
         }
     }
+    stamp();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc<512>(tmem);

@@ -12,6 +12,16 @@ constexpr int CK_THREADS = 512;  // 16 warps: TMEM lane quadrant = warp & 3, col
 __device__ int g_chunk_domain_err = 0;    // set when a chunk's accumulated decay leaves the fp32-safe range
 __device__ float* g_chunk_dbg = nullptr;  // development aid: CTA (0,0) records per-phase clocks of chunk 1
 
+// Shared-memory matrix descriptors built from the operand's byte offset inside the (1024-byte aligned) shared-memory
+// struct and b4 = (struct base address) >> 4: with compile-time offsets each descriptor is one integer add, which
+// matters because a single thread issues every tcgen05.mma of a phase (~100 per chunk in the backward).
+__device__ __forceinline__ uint64_t desc_km(uint32_t b4, uint32_t off_bytes) {  // K-major SWIZZLE_128B, 8-row groups 1024 B apart
+    return ((uint64_t)(64u | (1u << 14) | (2u << 29)) << 32) | (uint64_t)(b4 + (off_bytes >> 4) + (1u << 16));
+}
+__device__ __forceinline__ uint64_t desc_mn(uint32_t b4, uint32_t off_bytes, uint32_t lbo, uint32_t sbo = 512) {  // MN-major BASE32B
+    return ((uint64_t)((sbo >> 4) | (1u << 14) | (1u << 29)) << 32) | (uint64_t)(b4 + (off_bytes >> 4) + ((lbo >> 4) << 16));
+}
+
 // address of A[t][s] (fp32) in the chunk-swizzled 64x64 array `aab`: rows of 256 B, 16-byte chunks XOR (t & 7)
 __device__ __forceinline__ const float4* aab_chunk(const uint8_t* aab, int t, int chunk) {
     return reinterpret_cast<const float4*>(aab + t * 256 + ((chunk ^ (t & 7)) << 4));
