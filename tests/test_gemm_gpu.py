@@ -30,8 +30,9 @@ def test_gemm_matches_fp32_reference(M, N, K, epi):
     ref = _ref(a, w, epi, res)
     # one bf16 rounding of an fp32-accumulated result: |err| <= 2^-8 |ref| (+ a little for accumulation order)
     err = (c.float() - ref).abs()
-    # (relu^2: a pre-activation that sits on a bf16 rounding boundary may round the other way -> one more ulp, squared)
-    assert float((err - (2.0 ** -8) * ref.abs() * (3.0 if epi == 1 else 1.0)).max()) <= 2e-3
+    # (relu^2: a pre-activation that sits on a bf16 rounding boundary may round the other way (accumulation order) ->
+    #  one bf16 ulp of c, i.e. 2 ulp-fractions of c^2, on top of the final rounding; rare, so the RMS bound below stays tight)
+    assert float((err - (2.0 ** -8) * ref.abs() * (6.0 if epi == 1 else 1.0)).max()) <= 2e-3
     assert float(err.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt().clamp_min(1e-12)) < 2.5e-3
 
 

@@ -63,7 +63,7 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
 
     if (tid == 0) {
         mbar_init(&sm.bar_in, 1);
-        mbar_init(&sm.bar_mma, 1);
+        mbar_init(&sm.bar_mma, 2);  // two issuing threads (lane 0 of warps 0 and 1) commit every batch
         fence_mbar_init();
         tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k);
         tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b);
@@ -76,6 +76,7 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
     const uint32_t tmem = sm.tmem_base;
     const uint32_t tm_row = tmem + ((uint32_t)(32 * qd) << 16);
     constexpr uint32_t C_SC = 0, C_UY = 128, C_CORR = 192, C_TX = 320;
+    constexpr uint32_t C_SC2 = 320;  // second K-half of the scores (TX columns are free then); TX's second K-half uses C_SC
     // partial state sums of the four 16-step groups reuse the score / TX columns (both are dead by then)
     constexpr uint32_t C_R0 = 0, C_R1 = 64, C_R2 = 320, C_R3 = 384;
 
@@ -141,6 +142,15 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
         tc_fence_before();
         __syncthreads();
     };
+    // A single thread issues one tcgen05.mma per ~120 cycles whatever its size (scripts/ubench_mma_issue.cu); two threads
+    // feeding different accumulators reach one per ~62 cycles.  Every product batch is therefore split over two issuers,
+    // by accumulator where there are two, else by K range into two accumulators that the following phase adds.
+    const uint32_t b4 = smem_u32(&sm) >> 4;
+    const uint32_t O_IN = (uint32_t)(sm.in - (uint8_t*)&sm), O_AQ = (uint32_t)(sm.aq - (uint8_t*)&sm), O_BK = (uint32_t)(sm.bk - (uint8_t*)&sm),
+                   O_BK2 = (uint32_t)(sm.bk2 - (uint8_t*)&sm), O_UV = (uint32_t)(sm.uv - (uint8_t*)&sm), O_SB = (uint32_t)(sm.sb - (uint8_t*)&sm);
+    const uint32_t O_RMN = O_IN, O_TINV = O_IN + 32768, O_SC = O_BK;
+    const bool issuer = lane == 0 && warp < 2;
+    const int iw = warp;  // issuer index (valid when `issuer`)
     constexpr uint32_t ID_128x128 = umma_idesc_tf32(128, 128), ID_128x64 = umma_idesc_tf32(128, 64),
                        ID_B_MN_64 = umma_idesc_tf32(128, 64, 0, 1), ID_B_MN_128 = umma_idesc_tf32(128, 128, 0, 1),
                        ID_ST = umma_idesc_tf32(128, 64, 1, 1);
@@ -222,14 +232,11 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
         }
         operands_ready();
         // ================= scores =================
-        if (tid == 0) {
+        if (issuer) {  // issuer 0: channels 0-31 -> C_SC, issuer 1: channels 32-63 -> C_SC2 (added in P2)
             tc_fence_after();
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const uint64_t da = umma_desc_advance(umma_desc_sw128(sm.aq + (k >> 2) * 16384), (k & 3) * 32);
-                const uint64_t db = umma_desc_advance(umma_desc_sw128(sm.bk + (k >> 2) * 16384), (k & 3) * 32);
-                umma_tf32(tmem + C_SC, da, db, ID_128x128, k > 0);
-            }
+            for (int k = 0; k < 4; k++)
+                umma_tf32(tmem + (iw ? C_SC2 : C_SC), desc_km(b4, O_AQ + iw * 16384 + k * 32), desc_km(b4, O_BK + iw * 16384 + k * 32), ID_128x128, k > 0);
             umma_commit(&sm.bar_mma);
         }
         mma_wait(c);
@@ -240,13 +247,16 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
         {
             uint32_t v[32];
             const bool incl = r >= 64;  // q rows keep the diagonal
-            tmem_ld32(tm_row + C_SC + 32 * cs, v);
+            uint32_t v2[32];
+            tmem_ld32_nowait(tm_row + C_SC + 32 * cs, v);
+            tmem_ld32_nowait(tm_row + C_SC2 + 32 * cs, v2);
+            tmem_ld_wait();
             const int sbase = 32 * (cs & 1);
 #pragma unroll
             for (int e = 0; e < 32; e++) {
                 const int s = sbase + e;
                 const bool keep = incl ? (s <= t_r) : (s < t_r);
-                sc0[e] = keep ? __uint_as_float(v[e]) : 0.f;
+                sc0[e] = keep ? __uint_as_float(v[e]) + __uint_as_float(v2[e]) : 0.f;
             }
             if (cs < 2) {
                 if (r < 64) {
@@ -264,13 +274,12 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
         }
         operands_ready();
         // ================= ACC = [A_ak;A_qk] V (runs while the inverse is being computed) =================
-        if (tid == 0) {
+        if (issuer) {  // (hidden behind the inverse: one issuer is enough)
             tc_fence_after();
-            const uint64_t dbv = umma_desc_mn_tf32(sm.uv + 64 * 128, 16384, 512);
+            if (iw == 0) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const uint64_t da = umma_desc_advance(umma_desc_sw128(sc + (k >> 2) * 16384), (k & 3) * 32);
-                umma_tf32(tmem + C_UY, da, umma_desc_advance(dbv, k * 1024), ID_B_MN_64, k > 0);
+                for (int k = 0; k < 8; k++)
+                    umma_tf32(tmem + C_UY, desc_km(b4, O_SC + (k >> 2) * 16384 + (k & 3) * 32), desc_mn(b4, O_UV + 64 * 128 + k * 1024, 16384), ID_B_MN_64, k > 0);
             }
             umma_commit(&sm.bar_mma);
         }
@@ -305,42 +314,34 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
         }
         operands_ready();
         // ================= TX = Tinv [At | AV] =================
-        if (tid == 0) {
+        if (issuer) {  // issuer 0: s 0-31 -> C_TX, issuer 1: s 32-63 -> C_SC (the scores are dead); added in the next phase
             tc_fence_after();
-            const uint64_t dbr = umma_desc_mn_tf32(rmn, 8192, 512);
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const uint64_t da = umma_desc_advance(umma_desc_sw128(tinv + (k >> 2) * 8192), (k & 3) * 32);
-                umma_tf32(tmem + C_TX, da, umma_desc_advance(dbr, k * 1024), ID_B_MN_128, k > 0);
-            }
+            for (int k = 0; k < 4; k++)
+                umma_tf32(tmem + (iw ? C_SC : C_TX), desc_km(b4, O_TINV + iw * 8192 + k * 32), desc_mn(b4, O_RMN + (4 * iw + k) * 1024, 8192), ID_B_MN_128, k > 0);
             umma_commit(&sm.bar_mma);
         }
         mma_wait(c);
         // ================= [Ah | Uh] -> rmn (row-major, read MN-major by the next products) =================
         if (r < 64) {
-            uint32_t v[32];
-            tmem_ld32(tm_row + C_TX + 32 * cs, v);
+            uint32_t v[32], v2[32];
+            tmem_ld32_nowait(tm_row + C_TX + 32 * cs, v);
+            tmem_ld32_nowait(tm_row + C_SC + 32 * cs, v2);
+            tmem_ld_wait();
 #pragma unroll
             for (int cc = 0; cc < 8; cc++)
                 *reinterpret_cast<float4*>(rmn + cs * 8192 + sw32_off(r, 4 * cc)) =
-                    rt32(make_float4(__uint_as_float(v[4 * cc]), __uint_as_float(v[4 * cc + 1]), __uint_as_float(v[4 * cc + 2]),
-                                     __uint_as_float(v[4 * cc + 3])));
+                    rt32(make_float4(__uint_as_float(v[4 * cc]) + __uint_as_float(v2[4 * cc]), __uint_as_float(v[4 * cc + 1]) + __uint_as_float(v2[4 * cc + 1]),
+                                     __uint_as_float(v[4 * cc + 2]) + __uint_as_float(v2[4 * cc + 2]), __uint_as_float(v[4 * cc + 3]) + __uint_as_float(v2[4 * cc + 3])));
         }
         operands_ready();
         // ================= CORR = [A_ab;A_qb] Ah ;  ACC += [A_ab;A_qb] Uh =================
-        if (tid == 0) {
+        if (issuer) {  // issuer 0: CORR, issuer 1: ACC
             tc_fence_after();
-            const uint64_t dbh = umma_desc_mn_tf32(rmn, 8192, 512), dbu = umma_desc_mn_tf32(rmn + 2 * 8192, 8192, 512);
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const uint64_t da = umma_desc_advance(umma_desc_sw128(sc + (k >> 2) * 16384), (k & 3) * 32);
-                umma_tf32(tmem + C_CORR, da, umma_desc_advance(dbh, k * 1024), ID_B_MN_64, k > 0);
-            }
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const uint64_t da = umma_desc_advance(umma_desc_sw128(sc + (k >> 2) * 16384), (k & 3) * 32);
-                umma_tf32(tmem + C_UY, da, umma_desc_advance(dbu, k * 1024), ID_B_MN_64, 1);
-            }
+            for (int k = 0; k < 8; k++)
+                umma_tf32(tmem + (iw ? C_UY : C_CORR), desc_km(b4, O_SC + (k >> 2) * 16384 + (k & 3) * 32),
+                          desc_mn(b4, O_RMN + iw * 2 * 8192 + k * 1024, 8192), ID_B_MN_64, iw ? 1 : (k > 0));
             umma_commit(&sm.bar_mma);
         }
         mma_wait(c);
@@ -364,20 +365,25 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
         }
         operands_ready();
         // ================= ACC += [Ah;Qp] S_0^T  ->  [U;Y] =================
-        if (tid == 0) {
+        if (issuer) {  // issuer 0: j 0-31 -> ACC, issuer 1: j 32-63 -> the CORR columns (consumed by P5); added in P6
             tc_fence_after();
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const uint64_t da = umma_desc_advance(umma_desc_sw128(sm.aq + (k >> 2) * 16384), (k & 3) * 32);
-                const uint64_t db = umma_desc_advance(umma_desc_sw128(sm.sb + (k >> 2) * 8192), (k & 3) * 32);
-                umma_tf32(tmem + C_UY, da, db, ID_128x64, 1);
-            }
+            for (int k = 0; k < 4; k++)
+                umma_tf32(tmem + (iw ? C_CORR : C_UY), desc_km(b4, O_AQ + iw * 16384 + k * 32), desc_km(b4, O_SB + iw * 8192 + k * 32), ID_128x64,
+                          iw ? (k > 0) : 1);
             umma_commit(&sm.bar_mma);
         }
         mma_wait(c);
         // ================= P6: U operand; then D_g = U_g^T Bt_g + V_g^T Kt_g; sa / y stores behind the barrier ====
         uint32_t uy[16];
-        tmem_ld16(tm_row + C_UY + 16 * cs, uy);
+        {
+            uint32_t u2[16];
+            tmem_ld16_nowait(tm_row + C_UY + 16 * cs, uy);
+            tmem_ld16_nowait(tm_row + C_CORR + 16 * cs, u2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; e++) uy[e] = __float_as_uint(__uint_as_float(uy[e]) + __uint_as_float(u2[e]));
+        }
         if (r < 64) {
 #pragma unroll
             for (int c4 = 0; c4 < 4; c4++)
@@ -386,19 +392,18 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
                                      __uint_as_float(uy[4 * c4 + 3])));
         }
         operands_ready();
-        if (tid == 0) {
+        if (issuer) {  // issuer 0: groups 0,1; issuer 1: groups 2,3
             tc_fence_after();
-            const uint64_t da = umma_desc_mn_tf32(sm.uv, 16384, 512);
-            const uint64_t db = umma_desc_mn_tf32(sm.bk2, 16384, 512);
             constexpr uint32_t creg[4] = {C_R0, C_R1, C_R2, C_R3};
 #pragma unroll
-            for (int g = 0; g < 4; g++)
+            for (int gg = 0; gg < 2; gg++)
 #pragma unroll
                 for (int part = 0; part < 2; part++)
 #pragma unroll
                     for (int x = 0; x < 2; x++) {
+                        const int g = 2 * iw + gg;
                         const uint32_t off = (uint32_t)(part * 64 + 16 * g + 8 * x) * 128;
-                        umma_tf32(tmem + creg[g], umma_desc_advance(da, off), umma_desc_advance(db, off), ID_ST, (part | x) != 0);
+                        umma_tf32(tmem + (iw ? creg[2 + gg] : creg[gg]), desc_mn(b4, O_UV + off, 16384), desc_mn(b4, O_BK2 + off, 16384), ID_ST, (part | x) != 0);
                     }
             umma_commit(&sm.bar_mma);
         }
