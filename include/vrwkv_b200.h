@@ -74,6 +74,10 @@ int vrwkv_wkv7_forward_state(int B, int T, int H, const uint16_t* w, const uint1
  * tensor-core CTA per (batch, head, chunk) for the chunk-local gradients.  Without it (the plain entry points above, which is what
  * torch.ops.wind_backstepping binds) the step-by-step kernels run for any w.  Same tensors, same contract. */
 #define VRWKV_WKV7_BOUNDED_DECAY 1u
+/* With BOUNDED_DECAY only (T % 64 == 0, no carried state): s is f32 [B,H,T/64,64,64] and holds one transposed state per
+ * 64-step chunk (after step 64c+63) instead of the reference's T/16 checkpoints — all the chunked backward reads; a
+ * quarter of the memory and of the forward's checkpoint writes.  Pass the same flag to forward_ex and backward_ex. */
+#define VRWKV_WKV7_CHUNK_CHECKPOINTS 2u
 int vrwkv_wkv7_forward_ex(int B, int T, int H, const uint16_t* w, const uint16_t* q,
                           const uint16_t* k, const uint16_t* v, const uint16_t* a,
                           const uint16_t* b, uint16_t* y, float* s, float* sa,

@@ -238,3 +238,24 @@ def test_bounded_decay_autograd_and_domain_check():
     with pytest.raises(RuntimeError):
         W.domain_check()
     W.domain_check()  # the flag is cleared by the failed check
+
+
+def test_chunk_granularity_checkpoints_give_the_same_gradients():
+    """VRWKV_WKV7_CHUNK_CHECKPOINTS: one state per 64-step chunk; y is bit-identical, the chunked backward reads the same
+    boundary states from the smaller tensor."""
+    from visualrwkv_b200 import wkv7 as W
+    cpu = O.make_inputs(2, 256, 3, 64, seed=31)
+    w, q, k, v, a, b, dy = [x.cuda() for x in cpu]
+    y0, s0, sa0 = W.forward_raw(w, q, k, v, a, b, bounded_decay=True)
+    y1, s1, sa1 = W.forward_raw(w, q, k, v, a, b, bounded_decay=True, chunk_checkpoints=True)
+    assert s0.shape[2] == 16 and s1.shape[2] == 4
+    assert torch.equal(y0, y1) and torch.equal(sa0, sa1) and torch.equal(s1, s0[:, :, 3::4])
+    g0 = W.backward_raw(w, q, k, v, a, b, dy, s0, sa0, bounded_decay=True)
+    g1 = W.backward_raw(w, q, k, v, a, b, dy, s1, sa1, bounded_decay=True)
+    for x0, x1 in zip(g0, g1):
+        assert torch.equal(x0, x1)
+    with pytest.raises(RuntimeError):  # the flag without the promise is refused
+        from visualrwkv_b200 import _lib
+        _lib.check(_lib.lib().vrwkv_wkv7_forward_ex(2, 256, 3, _lib.ptr(w), _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(a),
+                                                    _lib.ptr(b), _lib.ptr(y1), _lib.ptr(s1), _lib.ptr(sa1), None, None,
+                                                    ctypes.c_uint(2), _lib.cur_stream()), "forward_ex")

@@ -21,7 +21,9 @@ struct Wkv7ChunkBwdArgs {
     int B, T, H;
     const uint16_t *w, *q, *k, *v, *a, *b, *dy;  // for the direct (non-TMA) re-reads
     const float* sa;                             // [B,T,H,64]
-    const float* s;                              // [B,H,T/16,64,64] transposed checkpoints
+    const float* s;                              // transposed state checkpoints, `ck_per_chunk` per 64-step chunk (4: the
+                                                 // reference's [B,H,T/16,64,64]; 1: [B,H,T/64,64,64] chunk-end states only)
+    int ck_per_chunk;
     const float* ds;                             // [B,H,T/64,64,64] dL/dS at the end of each chunk (last: not read)
     float* gws;                                  // [B,H,T/64,64,64] scratch: G_t of every chunk
     uint16_t *dw, *dq, *dk, *dv, *da, *db;
@@ -107,7 +109,7 @@ wkv7_chunk_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
         const int t = tid >> 3, i0 = 8 * (tid & 7);
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p.sa + row0 + (size_t)t * rstride + i0));
         if (c > 0)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.s + ((((size_t)bb * H + hh) * (T / WKV_TC) + (size_t)c * 4 - 1) * N + t) * N + i0));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.s + ((((size_t)bb * H + hh) * nch * p.ck_per_chunk + (size_t)c * p.ck_per_chunk - 1) * N + t) * N + i0));
     }
     uint32_t mph = 0;
     auto mma_wait = [&]() {
@@ -306,7 +308,7 @@ wkv7_chunk_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
     const float4 g_u1 = __ldg(reinterpret_cast<const float4*>(p.sa + row0 + (size_t)dt * rstride + di0) + 1);
     float4 g_s0 = make_float4(0.f, 0.f, 0.f, 0.f), g_s1 = g_s0;
     if (c > 0) {  // S_0: checkpoint memory [j][i] holds S_ij (wkv7_cuda.cu:44-50) = K-major (N = j, K = i)
-        const float4* ss = reinterpret_cast<const float4*>(p.s + ((((size_t)bb * H + hh) * (T / WKV_TC) + (size_t)c * 4 - 1) * N + dt) * N + di0);
+        const float4* ss = reinterpret_cast<const float4*>(p.s + ((((size_t)bb * H + hh) * nch * p.ck_per_chunk + (size_t)c * p.ck_per_chunk - 1) * N + dt) * N + di0);
         g_s0 = __ldg(ss);
         g_s1 = __ldg(ss + 1);
     }
@@ -521,7 +523,7 @@ wkv7_chunk_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
         const int j = tid & 63, ig = tid >> 6;
         float acc = 0.f;
         if (c + 1 < nch) {
-            const float* ck = p.s + ((((size_t)bb * H + hh) * (T / WKV_TC) + (size_t)c * 4 + 3) * N + j) * N + 8 * ig;
+            const float* ck = p.s + ((((size_t)bb * H + hh) * nch * p.ck_per_chunk + (size_t)(c + 1) * p.ck_per_chunk - 1) * N + j) * N + 8 * ig;
             const float4 s0 = __ldg(reinterpret_cast<const float4*>(ck)), s1 = __ldg(reinterpret_cast<const float4*>(ck) + 1);
             const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
             const float* dsl = p.ds + chunk_id * (N * N) + (size_t)(8 * ig) * N + j;

@@ -40,6 +40,9 @@ struct alignas(1024) Wkv7ChunkSmem {
     uint32_t tmem_base;
 };
 
+// CHUNK_CK: s holds one (transposed) state per 64-step chunk, s[b][h][c] = S after step 64c+63 — all the chunk-local
+// backward reads — instead of the reference's four 16-step checkpoints per chunk (3/4 of the forward's DRAM writes).
+template <bool CHUNK_CK>
 __global__ void __launch_bounds__(CK_THREADS, 1)
 wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_q,
                       const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
@@ -184,7 +187,7 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
 
     for (int c = 0; c < nch; c++) {
         stamp(c);
-        if (c > 0) write_checkpoints(c - 1);
+        if (!CHUNK_CK && c > 0) write_checkpoints(c - 1);
         mbar_wait(&sm.bar_in, c & 1);
         stamp(c);
         // ================= P1: decay prefix sums and scaled operands (8 rows x 1 column per thread) =================
@@ -453,11 +456,16 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
                 *reinterpret_cast<float4*>(sm.sb + (cs >> 1) * 8192 + r * 128 + ((ch ^ (r & 7)) << 4)) =
                     rt32(make_float4(Sprev[4 * c4], Sprev[4 * c4 + 1], Sprev[4 * c4 + 2], Sprev[4 * c4 + 3]));
             }
+            if (CHUNK_CK && p.s) {
+                float* ck = p.s + ((((size_t)bb * H + hh) * nch + (size_t)c) * N + 16 * cs) * N + r;
+#pragma unroll
+                for (int e = 0; e < 16; e++) ck[(size_t)e * N] = Sprev[e];  // transposed [j][i], like the 16-step checkpoints
+            }
         }
-        if (tid < 4 * N) sm.eck[tid >> 6][tid & 63] = sm.echk[tid >> 6][tid & 63];
+        if (!CHUNK_CK && tid < 4 * N) sm.eck[tid >> 6][tid & 63] = sm.echk[tid >> 6][tid & 63];
         operands_ready();
     }
-    write_checkpoints(nch - 1);
+    if (!CHUNK_CK) write_checkpoints(nch - 1);
     if (p.state_out && r < N) {
         float4* dst = reinterpret_cast<float4*>(p.state_out + (((size_t)bb * H + hh) * N + r) * N + 16 * cs);
 #pragma unroll

@@ -64,7 +64,7 @@ extern "C" int vrwkv_wkv7_chunk_debug(float* buf) {
     return VRWKV_OK;
 }
 
-static int launch_chunk_fwd(const void* const* in, const Wkv7FwdArgs& a, cudaStream_t st) {
+static int launch_chunk_fwd(const void* const* in, const Wkv7FwdArgs& a, bool chunk_ck, cudaStream_t st) {
     CUtensorMap tm[6];
     for (int i = 0; i < 6; i++) {
         int rc = vrwkv_encode_2d(&tm[i], in[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)a.H * WKV_N, (uint64_t)a.B * a.T,
@@ -72,9 +72,10 @@ static int launch_chunk_fwd(const void* const* in, const Wkv7FwdArgs& a, cudaStr
         if (rc) return rc;
     }
     const size_t smem = sizeof(Wkv7ChunkSmem) + 1024;
-    VRWKV_CUDA(cudaFuncSetAttribute(wkv7_chunk_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = chunk_ck ? wkv7_chunk_fwd_kernel<true> : wkv7_chunk_fwd_kernel<false>;
+    VRWKV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(a.H, a.B), block(CK_THREADS);
-    wkv7_chunk_fwd_kernel<<<grid, block, smem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], a);
+    kern<<<grid, block, smem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], a);
     VRWKV_CUDA(cudaGetLastError());
     vrwkv_count_launch(1);
     return VRWKV_OK;
@@ -151,7 +152,8 @@ static int ensure_pool_keeps_memory() {
 
 // backward entirely on the tensor cores: dS boundary scan, then one CTA per (batch, head, chunk)
 static int launch_bwd_chunked(const uint16_t* w, const uint16_t* q, const uint16_t* k, const uint16_t* v, const uint16_t* a,
-                              const uint16_t* b, const uint16_t* dy, const float* sa, const Wkv7BwdArgs& args, cudaStream_t st) {
+                              const uint16_t* b, const uint16_t* dy, const float* sa, const Wkv7BwdArgs& args, int ck_per_chunk,
+                              cudaStream_t st) {
     const int B = args.B, T = args.T, H = args.H, nch = T / CK_L;
     int rc = ensure_pool_keeps_memory();
     if (rc) return rc;
@@ -172,7 +174,7 @@ static int launch_bwd_chunked(const uint16_t* w, const uint16_t* q, const uint16
     }
     const size_t smem = sizeof(Wkv7ChunkBwdSmem) + 1024;
     VRWKV_CUDA(cudaFuncSetAttribute(wkv7_chunk_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    Wkv7ChunkBwdArgs ca{B, T, H, w, q, k, v, a, b, dy, sa, args.s, ws, ws + nstate, args.dw, args.dq, args.dk, args.dv, args.da, args.db};
+    Wkv7ChunkBwdArgs ca{B, T, H, w, q, k, v, a, b, dy, sa, args.s, ck_per_chunk, ws, ws + nstate, args.dw, args.dq, args.dk, args.dv, args.da, args.db};
     wkv7_chunk_bwd_kernel<<<dim3(H, B, nch), CK_THREADS, smem, st>>>(cm[0], cm[1], cm[2], cm[3], cm[4], cm[5], cm[6], ca);
     VRWKV_CUDA(cudaGetLastError());
     vrwkv_count_launch(1);
@@ -224,9 +226,14 @@ extern "C" int vrwkv_wkv7_forward_ex(int B, int T, int H, const uint16_t* w, con
     cudaStream_t st = (cudaStream_t)stream;
     int var = g_fwd_variant.load();
     if (var == 0) var = ((flags | default_flags()) & VRWKV_WKV7_BOUNDED_DECAY) ? 3 : 1;
+    if (flags & VRWKV_WKV7_CHUNK_CHECKPOINTS) {
+        if (!(flags & VRWKV_WKV7_BOUNDED_DECAY) || (T % CK_L) != 0 || state_in || state_out)
+            return vrwkv_fail(VRWKV_EINVAL, "wkv7 forward: CHUNK_CHECKPOINTS needs BOUNDED_DECAY, T %% 64 == 0 and no carried state");
+        var = 3;
+    }
     if (var == 3 && (T % CK_L) != 0) var = 1;  // the chunked kernel walks 64 steps at a time
     switch (var) {
-        case 3: return launch_chunk_fwd(in, args, st);  // tensor-core chunked evaluation (needs sum_chunk exp(w) < ~85)
+        case 3: return launch_chunk_fwd(in, args, (flags & VRWKV_WKV7_CHUNK_CHECKPOINTS) != 0, st);  // tensor cores (bounded decay)
         case 1: return launch_fwd2<4, 4>(tm, args, st);  // 4 rows x 8 columns per thread, 4 compute warps
         case 2: return launch_fwd2<2, 4>(tm, args, st);  // 2 rows x 8 columns per thread, 8 compute warps
         default: return vrwkv_fail(VRWKV_EINVAL, "wkv7 forward: unknown variant %d", var);
@@ -264,9 +271,13 @@ extern "C" int vrwkv_wkv7_backward_ex(int B, int T, int H, const uint16_t* w, co
     cudaStream_t st = (cudaStream_t)stream;
     int var = g_bwd_variant.load();
     if (var == 0) var = ((flags | default_flags()) & VRWKV_WKV7_BOUNDED_DECAY) ? 5 : 1;
+    if (flags & VRWKV_WKV7_CHUNK_CHECKPOINTS) {
+        if (!(flags & VRWKV_WKV7_BOUNDED_DECAY) || (T % CK_L) != 0 || var != 5)
+            return vrwkv_fail(VRWKV_EINVAL, "wkv7 backward: CHUNK_CHECKPOINTS needs BOUNDED_DECAY, T %% 64 == 0 and the chunked kernel");
+    }
     if ((var == 3 || var == 4 || var == 5) && (T % CK_L) != 0) var = 1;
     switch (var) {
-        case 5: return launch_bwd_chunked(w, q, k, v, a, b, dy, sa, args, st);  // tensor cores only (bounded decay)
+        case 5: return launch_bwd_chunked(w, q, k, v, a, b, dy, sa, args, (flags & VRWKV_WKV7_CHUNK_CHECKPOINTS) ? 1 : CK_L / WKV_TC, st);
         case 3: return launch_bwd_segmented<4, 3>(tm, w, q, a, b, dy, args, st);  // needs sum_chunk exp(w) < ~85
         case 4: return launch_bwd_segmented<2, 3>(tm, w, q, a, b, dy, args, st);  // same, 2 rows per thread (8 compute warps)
         case 1: return launch_bwd2<4, 3>(tm, args, st);

@@ -163,7 +163,7 @@ def relu_sq_backward_from_act(act, dy):
 def wkv7_fwd_raw(w, q, k, v, a, b):
     """[B,T,H,64] bf16 x6 -> y, s, sa.  The fused time-mix block builds w = -softplus(.) - 0.5 itself
     (tmix_mid_fwd_kernel, model.py:176), so it may promise bounded decay (include/vrwkv_b200.h)."""
-    return _wkv7.forward_raw(w, q, k, v, a, b, bounded_decay=True)
+    return _wkv7.forward_raw(w, q, k, v, a, b, bounded_decay=True, chunk_checkpoints=True)
 
 
 def wkv7_bwd_raw(w, q, k, v, a, b, dy, s, sa):

@@ -38,27 +38,35 @@ def launch_count() -> int:
     return int(L.vrwkv_launch_count())
 
 
-BOUNDED_DECAY = 1  # include/vrwkv_b200.h: VRWKV_WKV7_BOUNDED_DECAY
+BOUNDED_DECAY = 1      # include/vrwkv_b200.h: VRWKV_WKV7_BOUNDED_DECAY
+CHUNK_CHECKPOINTS = 2  # VRWKV_WKV7_CHUNK_CHECKPOINTS
+CHUNK = 64
 
 
-def forward_raw(w, q, k, v, a, b, bounded_decay: bool = False):
+def _flags(bounded_decay, chunk_checkpoints):
+    return ctypes.c_uint((BOUNDED_DECAY if bounded_decay else 0) | (CHUNK_CHECKPOINTS if chunk_checkpoints else 0))
+
+
+def forward_raw(w, q, k, v, a, b, bounded_decay: bool = False, chunk_checkpoints: bool = False):
     """[B,T,H,64] bf16 x6 (kernel order) -> y, s, sa through the C ABI (vrwkv_wkv7_forward_ex).
 
     bounded_decay=True is the caller's promise that exp(w) <= 0.607 (RWKV-7's w = -softplus(.) - 0.5, model.py:176);
-    it lets the library use the chunked tensor-core kernels."""
+    it lets the library use the chunked tensor-core kernels.  chunk_checkpoints=True (needs bounded_decay, T % 64 == 0):
+    s is [B,H,T/64,64,64], one state per chunk — pass the same to backward_raw."""
     L = _lib.lib()
     B, T, H, C = w.shape
     assert C == 64 and T % CHUNK_LEN == 0
     assert all(i.dtype == torch.bfloat16 and i.is_contiguous() and i.is_cuda for i in [w, q, k, v, a, b])
     y = torch.empty_like(v)
-    s = torch.empty(B, H, T // CHUNK_LEN, C, C, dtype=torch.float32, device=w.device)
+    chunk_checkpoints = bool(chunk_checkpoints and bounded_decay and T % CHUNK == 0)
+    s = torch.empty(B, H, T // (CHUNK if chunk_checkpoints else CHUNK_LEN), C, C, dtype=torch.float32, device=w.device)
     sa = torch.empty(B, T, H, C, dtype=torch.float32, device=w.device)
 
     def run():
         with torch.cuda.device(w.device):
             rc = L.vrwkv_wkv7_forward_ex(B, T, H, _lib.ptr(w), _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(a),
                                          _lib.ptr(b), _lib.ptr(y), _lib.ptr(s), _lib.ptr(sa), None, None,
-                                         ctypes.c_uint(BOUNDED_DECAY if bounded_decay else 0), _lib.cur_stream())
+                                         _flags(bounded_decay, chunk_checkpoints), _lib.cur_stream())
         _lib.check(rc, "vrwkv_wkv7_forward_ex")
 
     _timed("fwd", run)
@@ -66,9 +74,11 @@ def forward_raw(w, q, k, v, a, b, bounded_decay: bool = False):
 
 
 def backward_raw(w, q, k, v, a, b, dy, s, sa, bounded_decay: bool = False):
-    """Returns dw, dq, dk, dv, da, db (bf16 [B,T,H,64]) through vrwkv_wkv7_backward_ex."""
+    """Returns dw, dq, dk, dv, da, db (bf16 [B,T,H,64]) through vrwkv_wkv7_backward_ex (the checkpoint granularity is
+    read off the shape of s)."""
     L = _lib.lib()
     B, T, H, C = w.shape
+    chunk_checkpoints = s.shape[2] * CHUNK == T and s.shape[2] * CHUNK_LEN != T
     assert dy.dtype == torch.bfloat16 and dy.is_contiguous()
     outs = [torch.empty_like(w) for _ in range(6)]
 
@@ -77,7 +87,7 @@ def backward_raw(w, q, k, v, a, b, dy, s, sa, bounded_decay: bool = False):
             rc = L.vrwkv_wkv7_backward_ex(B, T, H, _lib.ptr(w), _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(a),
                                           _lib.ptr(b), _lib.ptr(dy), _lib.ptr(s), _lib.ptr(sa),
                                           *[_lib.ptr(o) for o in outs],
-                                          ctypes.c_uint(BOUNDED_DECAY if bounded_decay else 0), _lib.cur_stream())
+                                          _flags(bounded_decay, chunk_checkpoints), _lib.cur_stream())
         _lib.check(rc, "vrwkv_wkv7_backward_ex")
 
     _timed("bwd", run)
