@@ -50,7 +50,7 @@ def load_peaks():
 # --------------------------------------------------------------------------------------------------
 # CPU baseline (oracle port) — shared by cpu_baseline and --impl reference
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps: int, warmup: int, T: int = 128, B: int = 1, n_img_tok: int = 32):
+def cpu_reference_run(steps: int, warmup: int, T: int = 128, B: int = 1, n_img_tok: int = 36):
     """fp32 restatement of the same model (0.1B + SigLIP-B/16@224) on the host cores, fwd+bwd, on a bounded
     sample: B x T tokens with n_img_tok image tokens (196 patches pooled to n_img_tok)."""
     from oracle import model_ref as MR
