@@ -33,9 +33,9 @@ import torch  # noqa: E402
 
 WKV_FWD_BYTES_PER_ELEM = 14  # 6 bf16 reads + 1 bf16 write
 WKV_BWD_BYTES_PER_ELEM = 26  # 7 bf16 reads + 6 bf16 writes
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at cfg2 (B8 T2048 C768), ncu --set full, profiles/r1d_*:
-NCU_TRAFFIC_FWD = int((151.289 + 224.171) * 1e6)                      # wkv7_chunk_fwd_kernel (sa + s checkpoints: 250 MB of writes)
-NCU_TRAFFIC_BWD = int((121.960 + 23.555 + 324.474 + 168.567) * 1e6)   # dstate scan + chunk-local backward (incl. 50 MB G scratch)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at cfg2 (B8 T2048 C768), ncu --set full, profiles/r1e_*:
+NCU_TRAFFIC_FWD = int((151.359 + 83.432) * 1e6)                       # wkv7_chunk_fwd_kernel<chunk checkpoints> (y 25 + sa 50 + s 50 MB of writes)
+NCU_TRAFFIC_BWD = int((121.974 + 22.821 + 324.469 + 168.727) * 1e6)   # dstate scan + chunk-local backward (incl. 50 MB G scratch)
 
 
 def load_peaks():
@@ -236,7 +236,7 @@ def main():
         if fwd and bwd:
             fms, bms = sum(fwd) / len(fwd), sum(bwd) / len(bwd)
             peak = peaks["hbm_gbs"]
-            # DRAM bytes per launch from the ncu --set full capture of this configuration (profiles/r1d_wkv7_tc_summary.csv)
+            # DRAM bytes per launch from the ncu --set full capture of this configuration (profiles/r1e_wkv7_tc_model_path_summary.csv)
             line["roofline"] = {"kernel": "wkv7 backward = wkv7_chunk_dstate_kernel + wkv7_chunk_bwd_kernel", "bound": "hbm", "achieved": WKV_BWD_BYTES_PER_ELEM * nel / bms / 1e6,
                                 "peak": peak, "unit": "GB/s", "frac": WKV_BWD_BYTES_PER_ELEM * nel / bms / 1e6 / peak,
                                 "traffic": NCU_TRAFFIC_BWD if (B, T, args.n_embd) == (8, 2048, 768) else None, "traffic_unit": "bytes",

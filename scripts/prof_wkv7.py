@@ -14,8 +14,13 @@ y = torch.empty_like(v)
 s = torch.empty(B, H, T // 16, 64, 64, dtype=torch.float32, device="cuda")
 sa = torch.empty(B, T, H, 64, dtype=torch.float32, device="cuda")
 g = [torch.empty_like(w) for _ in range(6)]
-W.set_variant(fv, bv)
-for _ in range(3):
-    torch.ops.wind_backstepping.forward(w, q, k, v, a, b, y, s, sa)
-    torch.ops.wind_backstepping.backward(w, q, k, v, a, b, dy, s, sa, *g)
+if fv == 0 and bv == 0:  # the model path: bounded decay, chunk-granularity checkpoints
+    for _ in range(3):
+        y, s, sa = W.forward_raw(w, q, k, v, a, b, bounded_decay=True, chunk_checkpoints=True)
+        g = W.backward_raw(w, q, k, v, a, b, dy, s, sa, bounded_decay=True)
+else:
+    W.set_variant(fv, bv)
+    for _ in range(3):
+        torch.ops.wind_backstepping.forward(w, q, k, v, a, b, y, s, sa)
+        torch.ops.wind_backstepping.backward(w, q, k, v, a, b, dy, s, sa, *g)
 torch.cuda.synchronize()
