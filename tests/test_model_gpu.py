@@ -128,3 +128,27 @@ def test_vit_matches_hf_siglip_on_gpu():
     out = tower.to("cuda", torch.bfloat16)(px.to("cuda", torch.bfloat16))
     assert out.shape == ref.shape
     assert _rel(out, ref) < 3e-2
+
+
+def test_bench_line_keys():
+    """The GPU arm of bench.py on a reduced configuration (2 layers, ctx 1024, batch 2): one JSON line carrying the
+    contract's keys, a non-zero launch count of this library's kernels and the roofline object of the WKV7 pair."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "2", "--warmup", "3", "--no-cpu-baseline",
+                          "--layers", "2", "--ctx", "1024", "--batch", "2"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
+        assert k in d, k
+    assert d["gpu_launches"] > 0 and d["value"] > 0 and d["e2e"]["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] == 4
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and 0 < r["frac"] < 1 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert "chunk" in r["kernel"]  # the model path promises bounded decay: tensor-core kernels
