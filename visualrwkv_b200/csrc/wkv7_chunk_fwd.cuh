@@ -14,8 +14,9 @@
 //   D_g     = U_g^T Bt_g + V_g^T Kt_g for the four 16-step groups g; S_{16(g+1)} = (S_0 + D_0 + .. + D_g) diag(exp(G))
 // Operand layouts: K-major operands use SWIZZLE_128B rows of 32 tf32; [Bt;Kt], [U;V] and [At|AV] -> [Ah|Uh] are
 // stored row-major [step][channel] in the SWIZZLE_128B_BASE32B layout and consumed MN-major, so nothing is transposed
-// by hand.  Every MMA is issued by thread 0 and followed by a commit that all threads wait for (the phases are
-// sequential; the tensor-core time per chunk is ~1.5k cycles, the rest is operand preparation on the CUDA cores).
+// by hand.  Each product batch is issued by lane 0 of warps 0 and 1 (two accumulators in flight, see the comment at the
+// issue sites) and followed by commits that all threads wait for: the phases are sequential, the tensor-core time per
+// chunk is a few thousand cycles, the rest is operand preparation on the CUDA cores (DESIGN.md 2.2b has the breakdown).
 // Domain: exp(+-G) must stay finite, i.e. sum over a chunk of exp(w) < ~85 — guaranteed by RWKV-7's
 // w = -softplus(.) - 0.5 (exp(w) <= 0.607, model.py:176); the host dispatcher keeps the step-by-step kernel for
 // callers that cannot promise that.
