@@ -8,8 +8,8 @@
 //   scores  = [At;Qt] [Bt;Kt]^T      (128x128x64)  -> A_ab, A_ak (strictly lower), A_qb, A_qk (lower triangular)
 //   ACC     = [A_ak;A_qk] V          (128x64x64)   rows 0-63: AV
 //   Tinv    = (I - A_ab)^-1          fp32 on the CUDA cores (chunk_tri_inverse: 16x16 blocks + two coupling levels)
-//   TX      = Tinv [At | AV]         (64x128x64)   = [Ah | Uh]
-//   CORR    = [A_ab;A_qb] Ah ;  ACC += [A_ab;A_qb] Uh          => [At;Qt] + CORR = [Ah;Qp],  ACC = [Uh; Y_intra]
+//   W       = [A_ab;A_qb] Tinv       (128x64x64)   stays in TMEM and is the A operand of the next two products
+//   CORR    = W At ;  ACC += W AV     (= [A_ab;A_qb][Ah | Uh])   => [At;Qt] + CORR = [Ah;Qp],  ACC = [Uh; Y_intra]
 //   ACC    += [Ah;Qp] S_0^T                                    => ACC = [U; Y]  (rows of U are the sa_t)
 //   D_g     = U_g^T Bt_g + V_g^T Kt_g for the four 16-step groups g; S_{16(g+1)} = (S_0 + D_0 + .. + D_g) diag(exp(G))
 // Operand layouts: K-major operands use SWIZZLE_128B rows of 32 tf32; [Bt;Kt], [U;V] and [At|AV] -> [Ah|Uh] are
@@ -37,7 +37,7 @@ struct alignas(1024) Wkv7ChunkSmem {
     float part[8][WKV_N];              // per row-group decay sums
     float echk[4][WKV_N];              // exp(G_t) at t = 15, 31, 47, 63
     float eck[4][WKV_N];               // the same for the previous chunk (its checkpoints are written one chunk late)
-    uint64_t bar_in, bar_mma;
+    uint64_t bar_in, bar_mma, bar_w;
     uint32_t tmem_base;
 };
 
@@ -53,7 +53,7 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
     extern __shared__ __align__(1024) uint8_t chunk_smem_bytes[];
     Wkv7ChunkSmem& sm = *reinterpret_cast<Wkv7ChunkSmem*>(chunk_smem_bytes);
     uint8_t* const rmn = sm.in;           // [At|AV] -> [Ah|Uh], MN-major: 4 channel blocks x 64 k-lines x 128 B
-    uint8_t* const tinv = sm.in + 32768;  // A operand Tinv (K-major): 2 k-atoms x 64 rows (rows 64-127 alias what follows)
+    uint8_t* const tinv = sm.in + 32768;  // Tinv [t][s] row-major, MN-major B operand: 2 column blocks x 64 k-lines
     uint8_t* const sc = sm.bk;            // A operand [A_ak;A_qk], then [A_ab;A_qb]
 
     const int hh = blockIdx.x, bb = blockIdx.y;
@@ -68,6 +68,7 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
     if (tid == 0) {
         mbar_init(&sm.bar_in, 1);
         mbar_init(&sm.bar_mma, 2);  // two issuing threads (lane 0 of warps 0 and 1) commit every batch
+        mbar_init(&sm.bar_w, 1);    // W = [A_ab;A_qb] Tinv complete (waited for by the two issuers only)
         fence_mbar_init();
         tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k);
         tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b);
@@ -80,7 +81,7 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
     const uint32_t tmem = sm.tmem_base;
     const uint32_t tm_row = tmem + ((uint32_t)(32 * qd) << 16);
     constexpr uint32_t C_SC = 0, C_UY = 128, C_CORR = 192, C_TX = 320;
-    constexpr uint32_t C_SC2 = 320;  // second K-half of the scores (TX columns are free then); TX's second K-half uses C_SC
+    constexpr uint32_t C_SC2 = 384;  // second K-half of the scores (free until the state products at the end of the chunk)
     // partial state sums of the four 16-step groups reuse the score / TX columns (both are dead by then)
     constexpr uint32_t C_R0 = 0, C_R1 = 64, C_R2 = 320, C_R3 = 384;
 
@@ -156,7 +157,7 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
     const bool issuer = lane == 0 && warp < 2;
     const int iw = warp;  // issuer index (valid when `issuer`)
     constexpr uint32_t ID_128x128 = umma_idesc_tf32(128, 128), ID_128x64 = umma_idesc_tf32(128, 64),
-                       ID_B_MN_64 = umma_idesc_tf32(128, 64, 0, 1), ID_B_MN_128 = umma_idesc_tf32(128, 128, 0, 1),
+                       ID_B_MN_64 = umma_idesc_tf32(128, 64, 0, 1),
                        ID_ST = umma_idesc_tf32(128, 64, 1, 1);
 
     // checkpoints of chunk c-1: written at the start of chunk c so that the stores drain behind P1 instead of in
@@ -298,7 +299,7 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
             }
         }
         // ================= Tinv = (I - A_ab)^-1 =================
-        chunk_tri_inverse(sm.aab, sm.esc, tid, [&](int t, int s) { return tinv + (s >> 5) * 8192 + sw128_off(t, s & 31); });
+        chunk_tri_inverse(sm.aab, sm.esc, tid, [&](int t, int s) { return tinv + (s >> 5) * 8192 + sw32_off(t, s & 31); });
         mma_wait(c);
         // ================= P3: AV -> rmn blocks 2,3; [A_ab;A_qb] operand =================
         if (r < 64) {
@@ -317,35 +318,23 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
                     rt32(make_float4(sc0[4 * cc], sc0[4 * cc + 1], sc0[4 * cc + 2], sc0[4 * cc + 3]));
         }
         operands_ready();
-        // ================= TX = Tinv [At | AV] =================
-        if (issuer) {  // issuer 0: s 0-31 -> C_TX, issuer 1: s 32-63 -> C_SC (the scores are dead); added in the next phase
+        // ================= W = [A_ab;A_qb] Tinv ;  CORR = W At ;  ACC += W AV   (W never leaves TMEM) =================
+        // (= [A_ab;A_qb] [Ah | Uh] with [Ah | Uh] = Tinv [At | AV]; the second product reads its A operand from the
+        //  accumulator columns of the first, scripts/ubench_mma_modes.cu)
+        if (issuer) {
             tc_fence_after();
+            if (iw == 0) {
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-                umma_tf32(tmem + (iw ? C_SC : C_TX), desc_km(b4, O_TINV + iw * 8192 + k * 32), desc_mn(b4, O_RMN + (4 * iw + k) * 1024, 8192), ID_B_MN_128, k > 0);
-            umma_commit(&sm.bar_mma);
-        }
-        mma_wait(c);
-        // ================= [Ah | Uh] -> rmn (row-major, read MN-major by the next products) =================
-        if (r < 64) {
-            uint32_t v[32], v2[32];
-            tmem_ld32_nowait(tm_row + C_TX + 32 * cs, v);
-            tmem_ld32_nowait(tm_row + C_SC + 32 * cs, v2);
-            tmem_ld_wait();
-#pragma unroll
-            for (int cc = 0; cc < 8; cc++)
-                *reinterpret_cast<float4*>(rmn + cs * 8192 + sw32_off(r, 4 * cc)) =
-                    rt32(make_float4(__uint_as_float(v[4 * cc]) + __uint_as_float(v2[4 * cc]), __uint_as_float(v[4 * cc + 1]) + __uint_as_float(v2[4 * cc + 1]),
-                                     __uint_as_float(v[4 * cc + 2]) + __uint_as_float(v2[4 * cc + 2]), __uint_as_float(v[4 * cc + 3]) + __uint_as_float(v2[4 * cc + 3])));
-        }
-        operands_ready();
-        // ================= CORR = [A_ab;A_qb] Ah ;  ACC += [A_ab;A_qb] Uh =================
-        if (issuer) {  // issuer 0: CORR, issuer 1: ACC
+                for (int k = 0; k < 8; k++)
+                    umma_tf32(tmem + C_TX, desc_km(b4, O_SC + (k >> 2) * 16384 + (k & 3) * 32), desc_mn(b4, O_TINV + k * 1024, 8192), ID_B_MN_64, k > 0);
+                umma_commit(&sm.bar_w);
+            }
+            mbar_wait(&sm.bar_w, c & 1);
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < 8; k++)
-                umma_tf32(tmem + (iw ? C_UY : C_CORR), desc_km(b4, O_SC + (k >> 2) * 16384 + (k & 3) * 32),
-                          desc_mn(b4, O_RMN + iw * 2 * 8192 + k * 1024, 8192), ID_B_MN_64, iw ? 1 : (k > 0));
+                umma_tf32_ts(tmem + (iw ? C_UY : C_CORR), tmem + C_TX + 8 * k, desc_mn(b4, O_RMN + iw * 2 * 8192 + k * 1024, 8192), ID_B_MN_64,
+                             iw ? 1 : (k > 0));
             umma_commit(&sm.bar_mma);
         }
         mma_wait(c);
