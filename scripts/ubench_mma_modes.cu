@@ -1,4 +1,5 @@
-// Two questions for the next round of the chunked WKV7 kernels (answers in DESIGN.md 2.2b):
+// Two questions for the chunked WKV7 kernels (answers in DESIGN.md 2.2b; NOTE: (1) passes here, 50/50 exact, yet the same
+// pattern inside wkv7_chunk_bwd_kernel gave wrong gradients — do not rely on it; (2) is used by the product kernels):
 //  (1) may two threads accumulate into the SAME TMEM accumulator concurrently (K range split over two issuers)?
 //  (2) does tcgen05.mma accept its A operand from TMEM for kind::tf32 (fp32 accumulator columns re-used as A)?
 // D[128x64] = A[128x64] * B[64x64]^T with small-integer data (exact in tf32); checked against a CPU product.

@@ -84,7 +84,8 @@ wkv7_chunk_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
     const uint32_t tm_row = tmem + ((uint32_t)(32 * qd) << 16);
-    constexpr uint32_t C_SC = 0, C_ACC1 = 128, C_R = 192, C_DA = 256, C_A = 384, C_Q = 448, C_BK = 0;
+    // TMEM columns: scores 0-127 (then dA^T), [dU;dV] 128-191, dR 192-255, dA 256-383, [dBt;dKt] 384-447, [dAt;dQt] 448-511
+    constexpr uint32_t C_SC = 0, C_ACC1 = 128, C_R = 192, C_DA = 256, C_DAT = 0, C_BK = 384, C_AQ = 448;
 
     if (tid == 0) {
         mbar_arrive_expect_tx(&sm.bar_in, 7 * L * N * 2);
@@ -354,72 +355,61 @@ wkv7_chunk_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
             for (int k = 0; k < 8; k++)
                 umma_tf32(tmem + C_DA, desc_km(b4, O_Z1 + (k >> 2) * 16384 + (k & 3) * 32), desc_km(b4, O_Z2 + (k >> 2) * 16384 + (k & 3) * 32),
                           ID_KK_128, k > 0);
-        } else if (warp == 1) {
+        } else if (warp == 1) {  // dA^T = [U;V] [dR;dY]^T (the transposed operand of dA^T [At;Qt] comes from a product, not a transpose)
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const uint64_t db = desc_km(b4, O_S0 + (k >> 2) * 8192 + (k & 3) * 32);
-                umma_tf32(tmem + C_A, desc_km(b4, O_Z1 + (k >> 2) * 16384 + (k & 3) * 32), db, ID_KK, k > 0);
-                umma_tf32(tmem + C_Q, desc_km(b4, O_Z1 + 64 * 128 + (k >> 2) * 16384 + (k & 3) * 32), db, ID_KK, k > 0);
-            }
+            for (int k = 0; k < 8; k++)
+                umma_tf32(tmem + C_DAT, desc_km(b4, O_Z2 + (k >> 2) * 16384 + (k & 3) * 32), desc_km(b4, O_Z1 + (k >> 2) * 16384 + (k & 3) * 32),
+                          ID_KK_128, k > 0);
         } else if (warp == 2) {
 #pragma unroll
-            for (int k = 0; k < 8; k++)
-                umma_tf32(tmem + C_BK, desc_km(b4, O_Z2 + (k >> 2) * 16384 + (k & 3) * 32), desc_mn(b4, O_DZ + k * 1024, 8192), ID_KM, k > 0);
+            for (int k = 0; k < 8; k++)  // [dAt;dQt] = [dR;dY] S_0
+                umma_tf32(tmem + C_AQ, desc_km(b4, O_Z1 + (k >> 2) * 16384 + (k & 3) * 32), desc_km(b4, O_S0 + (k >> 2) * 8192 + (k & 3) * 32), ID_KK, k > 0);
         } else {
 #pragma unroll
-            for (int k = 0; k < 8; k++)
+            for (int k = 0; k < 8; k++)  // dV += A_ak^T dR
                 umma_tf32(tmem + C_ACC1, desc_mn(b4, O_SA + k * 1024, 8192), desc_mn(b4, O_X16 + k * 1024, 8192), ID_MM, 1);
+#pragma unroll
+            for (int k = 0; k < 8; k++)  // [dBt;dKt] = [U;V] dZ
+                umma_tf32(tmem + C_BK, desc_km(b4, O_Z2 + (k >> 2) * 16384 + (k & 3) * 32), desc_mn(b4, O_DZ + k * 1024, 8192), ID_KM, k > 0);
         }
         umma_commit(&sm.bar_mma);
     }
     mma_wait();
-    // ================= epsilon: masked dA as operands (a rows -> z1 / z2, q rows -> sa_ / dz+x16), then both products =========
+    // ================= epsilon: dA and dA^T masked in place in TMEM, then fed back as A operands =================
     {
         uint32_t v[32];
-        stamp();
-        tmem_ld32(tm_row + C_DA + 32 * cs, v);
-        stamp();
         const int t = r & 63;
         const bool qrow = r >= 64;
-        uint8_t* const kdst = (qrow ? sm.sa_ : sm.z1) + cs * 8192 + t * 128;  // K-major: 4 k-atoms x 64 rows
-        uint8_t* const mdst = (qrow ? sm.dz : sm.z2) + cs * 8192;              // MN-major: 4 column blocks x 64 k-lines
+        tmem_ld32(tm_row + C_DA + 32 * cs, v);  // dA[row r][s'], s' = 32cs + e: columns 0-63 vs U (A_ab / A_qb), 64-127 vs V
 #pragma unroll
-        for (int c4 = 0; c4 < 8; c4++) {
-            float o[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const int s_ = 32 * (cs & 1) + 4 * c4 + e;
-                const bool keep = qrow ? (s_ <= t) : (s_ < t);
-                o[e] = keep ? rt32(__uint_as_float(v[4 * c4 + e])) : 0.f;
-            }
-            const float4 x = make_float4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<float4*>(kdst + ((c4 ^ (t & 7)) << 4)) = x;
-            *reinterpret_cast<float4*>(mdst + sw32_off(t, 4 * c4)) = x;
+        for (int e = 0; e < 32; e++) {
+            const int s_ = 32 * (cs & 1) + e;
+            const bool keep = qrow ? (s_ <= t) : (s_ < t);
+            v[e] = keep ? __float_as_uint(rt32(__uint_as_float(v[e]))) : 0u;
         }
+        tmem_st32(tm_row + C_DA + 32 * cs, v);
+        tmem_ld32(tm_row + C_DAT + 32 * cs, v);  // dA^T[row r = s'][column = a row t (0-63) or q row t (64-127)], s = r & 63
+#pragma unroll
+        for (int e = 0; e < 32; e++) {
+            const int tc = 32 * (cs & 1) + e;
+            const bool keep = (cs >= 2) ? (t <= tc) : (t < tc);
+            v[e] = keep ? __float_as_uint(rt32(__uint_as_float(v[e]))) : 0u;
+        }
+        tmem_st32(tm_row + C_DAT + 32 * cs, v);
+        tmem_st_wait();
     }
-    stamp();
-    fence_proxy_async();
-    stamp();
     tc_fence_before();
     __syncthreads();
-    stamp();
     if (issuer) {
         tc_fence_after();
-        if (warp == 0) {  // dAt += dA_a [Bt;Kt]      (one accumulator is fed by one issuing thread only)
+        // (one issuing thread per accumulator: splitting a K range over two threads that accumulate into the same TMEM
+        //  columns passed a micro-benchmark but produced wrong gradients here)
+        if (warp == 0) {  // [dAt;dQt] += dA [Bt;Kt]
 #pragma unroll
-            for (int k = 0; k < 16; k++)
-                umma_tf32(tmem + C_A, desc_km(b4, O_Z1 + (k >> 2) * 8192 + (k & 3) * 32), desc_mn(b4, O_BK + k * 1024, 16384), ID_KM, 1);
-        } else if (warp == 1) {  // dQt += dA_q [Bt;Kt]
+            for (int k = 0; k < 16; k++) umma_tf32_ts(tmem + C_AQ, tmem + C_DA + 8 * k, desc_mn(b4, O_BK + k * 1024, 16384), ID_KM, 1);
+        } else if (warp == 1) {  // [dBt;dKt] += dA^T [At;Qt]
 #pragma unroll
-            for (int k = 0; k < 16; k++)
-                umma_tf32(tmem + C_Q, desc_km(b4, O_SA + (k >> 2) * 8192 + (k & 3) * 32), desc_mn(b4, O_BK + k * 1024, 16384), ID_KM, 1);
-        } else if (warp == 2) {  // [dBt;dKt] += dA_a^T At + dA_q^T Qt
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-                umma_tf32(tmem + C_BK, desc_mn(b4, O_Z2 + k * 1024, 8192), desc_mn(b4, O_AQ + k * 1024, 16384), ID_MM, 1);
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-                umma_tf32(tmem + C_BK, desc_mn(b4, O_DZ + k * 1024, 8192), desc_mn(b4, O_AQ + 64 * 128 + k * 1024, 16384), ID_MM, 1);
+            for (int k = 0; k < 16; k++) umma_tf32_ts(tmem + C_BK, tmem + C_DAT + 8 * k, desc_mn(b4, O_AQ + k * 1024, 16384), ID_KM, 1);
         }
         umma_commit(&sm.bar_mma);
     }
@@ -429,22 +419,19 @@ wkv7_chunk_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
     const size_t ego = row0 + (size_t)et * rstride + ej0;
     const float* egrow = p.gws + chunk_id * (L * N) + et * N + ej0;
     float4 eG[4], eGm[4];
-    uint4 ein[3][2];
+    uint4 ein[2][2];
 #pragma unroll
     for (int c4 = 0; c4 < 4; c4++) {
         eG[c4] = *reinterpret_cast<const float4*>(egrow + 4 * c4);
         eGm[c4] = (r < 64 && et > 0) ? *reinterpret_cast<const float4*>(egrow - N + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    {
-        const uint16_t* src0 = (r >= 64) ? p.k : p.a;
+    {   // rows 0-63 finish da, db (need a, b); rows 64-127 finish dq, dk, dv (need q, k)
+        const uint16_t* src0 = (r >= 64) ? p.q : p.a;
+        const uint16_t* src1 = (r >= 64) ? p.k : p.b;
         ein[0][0] = __ldg(reinterpret_cast<const uint4*>(src0 + ego));
         ein[0][1] = __ldg(reinterpret_cast<const uint4*>(src0 + ego) + 1);
-        if (r < 64) {
-            ein[1][0] = __ldg(reinterpret_cast<const uint4*>(p.q + ego));
-            ein[1][1] = __ldg(reinterpret_cast<const uint4*>(p.q + ego) + 1);
-            ein[2][0] = __ldg(reinterpret_cast<const uint4*>(p.b + ego));
-            ein[2][1] = __ldg(reinterpret_cast<const uint4*>(p.b + ego) + 1);
-        }
+        ein[1][0] = __ldg(reinterpret_cast<const uint4*>(src1 + ego));
+        ein[1][1] = __ldg(reinterpret_cast<const uint4*>(src1 + ego) + 1);
     }
     mma_wait();
     // ================= epilogue =================
@@ -452,8 +439,8 @@ wkv7_chunk_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
     // three [64][64] fp32 scratch arrays with a row pitch of 65 floats: written row-wise by lanes that differ in t
     // (pitch 64 would put a whole warp on one bank), read column-wise by lanes that differ in j
     constexpr int EP = 65;
-    float* const kk_s = reinterpret_cast<float*>(sm.z1);              // (dk k)[t][j]
-    float* const p1_s = reinterpret_cast<float*>(sm.z1) + 64 * EP;    // (dq q - db b)[t][j]
+    float* const kk_s = reinterpret_cast<float*>(sm.z1);              // (db b)[t][j]
+    float* const p1_s = reinterpret_cast<float*>(sm.z1) + 64 * EP;    // (dq q - dk k)[t][j]
     float* const p2_s = reinterpret_cast<float*>(sm.z1) + 128 * EP;   // (da a)[t][j]   (runs on into z2)
     {
         const int t = et, j0 = ej0;
@@ -479,41 +466,41 @@ wkv7_chunk_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
             *reinterpret_cast<uint4*>(ptr) = u0;
             *(reinterpret_cast<uint4*>(ptr) + 1) = u1;
         };
-        if (r >= 64) {  // dk, dv
-            uint32_t vk[16], vv[16];
+        if (r >= 64) {  // dq, dk, dv
+            uint32_t vq[16], vk[16], vv[16];
+            tmem_ld16_nowait(tm_row + C_AQ + j0, vq);
             tmem_ld16_nowait(tm_row + C_BK + j0, vk);
             tmem_ld16_nowait(tm_row + C_ACC1 + j0, vv);
             tmem_ld_wait();
-            float kin[16], dk[16], dv[16];
-            un16(ein[0], kin);
+            float qin[16], kin[16], dq[16], dk[16], dv[16];
+            un16(ein[0], qin);
+            un16(ein[1], kin);
 #pragma unroll
             for (int e = 0; e < 16; e++) {
+                dq[e] = __uint_as_float(vq[e]) * __expf(G[e]);
                 dk[e] = __uint_as_float(vk[e]) * __expf(-G[e]);
                 dv[e] = __uint_as_float(vv[e]);
-                kk_s[t * EP + j0 + e] = dk[e] * kin[e];
+                p1_s[t * EP + j0 + e] = dq[e] * qin[e] - dk[e] * kin[e];
             }
+            st16(p.dq + go, dq);
             st16(p.dk + go, dk);
             st16(p.dv + go, dv);
-        } else {  // da, dq, db
-            uint32_t va[16], vq[16], vb[16];
-            tmem_ld16_nowait(tm_row + C_A + j0, va);
-            tmem_ld16_nowait(tm_row + C_Q + j0, vq);
+        } else {  // da, db
+            uint32_t va[16], vb[16];
+            tmem_ld16_nowait(tm_row + C_AQ + j0, va);
             tmem_ld16_nowait(tm_row + C_BK + j0, vb);
             tmem_ld_wait();
-            float ain[16], qin[16], bin[16], da[16], dq[16], db[16];
+            float ain[16], bin[16], da[16], db[16];
             un16(ein[0], ain);
-            un16(ein[1], qin);
-            un16(ein[2], bin);
+            un16(ein[1], bin);
 #pragma unroll
             for (int e = 0; e < 16; e++) {
                 da[e] = __uint_as_float(va[e]) * __expf(Gm[e]);
-                dq[e] = __uint_as_float(vq[e]) * __expf(G[e]);
                 db[e] = __uint_as_float(vb[e]) * __expf(-G[e]);
-                p1_s[t * EP + j0 + e] = dq[e] * qin[e] - db[e] * bin[e];
+                kk_s[t * EP + j0 + e] = db[e] * bin[e];
                 p2_s[t * EP + j0 + e] = da[e] * ain[e];
             }
             st16(p.da + go, da);
-            st16(p.dq + go, dq);
             st16(p.db + go, db);
         }
     }
