@@ -70,14 +70,17 @@ int vrwkv_wkv7_forward_state(int B, int T, int H, const uint16_t* w, const uint1
 /* Extended entry points: `flags` may carry VRWKV_WKV7_BOUNDED_DECAY, the caller's promise that exp(w) <= 0.607
  * everywhere — true for RWKV-7's w = -softplus(.) - 0.5 (VisualRWKV-v7/v7.00/src/model.py:176), i.e. for every call
  * RWKV_Tmix_x070 makes (model.py:190).  With it (and T % 64 == 0) the library evaluates the recurrence 64 steps at a
- * time on the tensor cores: forward = chunked kernel, backward = tensor-core scan of dL/dS at chunk boundaries + one
- * tensor-core CTA per (batch, head, chunk) for the chunk-local gradients.  Without it (the plain entry points above, which is what
- * torch.ops.wind_backstepping binds) the step-by-step kernels run for any w.  Same tensors, same contract. */
+ * time on the tensor cores at fp32-level accuracy (every product is split into bf16 parts, csrc/wkv7_x6_common.cuh):
+ * the outputs meet the same element-wise bounds as the step-by-step kernels.  Without it (the plain entry points above,
+ * which is what torch.ops.wind_backstepping binds) the step-by-step kernels run for any w.  Same tensors, same contract. */
 #define VRWKV_WKV7_BOUNDED_DECAY 1u
 /* With BOUNDED_DECAY only (T % 64 == 0, no carried state): s is f32 [B,H,T/64,64,64] and holds one transposed state per
  * 64-step chunk (after step 64c+63) instead of the reference's T/16 checkpoints — all the chunked backward reads; a
  * quarter of the memory and of the forward's checkpoint writes.  Pass the same flag to forward_ex and backward_ex. */
 #define VRWKV_WKV7_CHUNK_CHECKPOINTS 2u
+/* With BOUNDED_DECAY: use the round-1 single-pass TF32 tensor-core kernels instead (faster products, but sa / s only
+ * to ~5e-4 RMS: outside the north-star tolerance; kept for comparison, never a default). */
+#define VRWKV_WKV7_TF32 4u
 int vrwkv_wkv7_forward_ex(int B, int T, int H, const uint16_t* w, const uint16_t* q,
                           const uint16_t* k, const uint16_t* v, const uint16_t* a,
                           const uint16_t* b, uint16_t* y, float* s, float* sa,
@@ -93,9 +96,9 @@ int vrwkv_wkv7_domain_check(void);
 /* Development aid: per-phase clock stamps of the chunked forward kernel are written to buf (NULL disables). */
 int vrwkv_wkv7_chunk_debug(float* buf);
 
-/* Kernel-variant selection for benchmarking (0 = default heuristic; forward 1/2 step-by-step, 3 chunked;
- * backward 1/2 step-by-step, 3/4 dS scan + step-by-step kernel on 64-step segments, 5 dS scan + chunked tensor-core
- * kernel). Thread-safe, process-wide. */
+/* Kernel-variant selection for benchmarking (0 = default heuristic; forward 1/2 step-by-step, 3 TF32 chunked, 6 x6
+ * chunk-parallel; backward 1/2 step-by-step, 3/4 TF32 dS scan + step-by-step kernel on 64-step segments, 5 TF32 dS scan
+ * + chunked tensor-core kernel, 7 x3 chunked). Thread-safe, process-wide. */
 int vrwkv_wkv7_set_variant(int fwd_variant, int bwd_variant);
 
 

@@ -25,6 +25,10 @@ struct CeArgs {
     float l2;
 };
 
+// exp(m - nm) for the online-softmax merges; a partial that saw no element (m = -inf, s = 0) contributes exactly 0
+// (exp(-inf - -inf) would be NaN: rows shorter than 2048 leave whole lanes empty)
+__device__ __forceinline__ float ce_rescale(float m, float nm) { return m == -INFINITY ? 0.f : __expf(m - nm); }
+
 __global__ void __launch_bounds__(256) ce_fwd_kernel(const CeArgs a) {
     __shared__ float smax[8], ssum[8];
     __shared__ int sidx[8];
@@ -40,7 +44,7 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const CeArgs a) {
         for (int e = 1; e < 8; e++)
             if (v.v[e] > vm) { vm = v.v[e]; vi = e; }
         if (vm > m) {
-            s *= __expf(m - vm);
+            s *= ce_rescale(m, vm);
             m = vm;
             am = i + vi;
         }
@@ -53,7 +57,7 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const CeArgs a) {
         const float om = __shfl_xor_sync(0xffffffffu, m, o), os = __shfl_xor_sync(0xffffffffu, s, o);
         const int oi = __shfl_xor_sync(0xffffffffu, am, o);
         const float nm = fmaxf(m, om);
-        s = s * __expf(m - nm) + os * __expf(om - nm);
+        s = s * ce_rescale(m, nm) + os * ce_rescale(om, nm);
         if (om > m || (om == m && oi < am)) am = oi;
         m = nm;
     }
@@ -64,7 +68,7 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const CeArgs a) {
         int A = sidx[0];
         for (int w = 1; w < 8; w++) {
             const float nm = fmaxf(M, smax[w]);
-            S = S * __expf(M - nm) + ssum[w] * __expf(smax[w] - nm);
+            S = S * ce_rescale(M, nm) + ssum[w] * ce_rescale(smax[w], nm);
             if (smax[w] > M || (smax[w] == M && sidx[w] < A)) A = sidx[w];
             M = nm;
         }

@@ -28,6 +28,12 @@
 namespace vrwkv {
 
 constexpr int GM_BM = 128, GM_BK = 64, GM_STAGES = 4;
+
+__device__ __forceinline__ bool elect_one_lane() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 enum { GM_EPI_NONE = 0, GM_EPI_RELU_SQ = 1, GM_EPI_ADD = 2 };
 
 struct GemmArgs {
@@ -79,7 +85,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one_lane()) {
             tma_prefetch_desc(&tm_a);
             tma_prefetch_desc(&tm_b);
             int it = 0;  // running k-block counter across tiles (ring position)
@@ -96,7 +102,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // (elect.sync, not `lane == 0`: only then does the compiler treat the descriptor / TMEM-address operands as
+        //  warp-uniform and issue tcgen05.mma back to back instead of inside a vote/elect/R2UR loop of ~120 cycles)
+        if (elect_one_lane()) {
             // instruction descriptor (kind::f16): D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GM_BM >> 4) << 24);
             int it = 0, lt = 0;  // lt: local tile counter

@@ -151,3 +151,50 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 __device__ __forceinline__ float rt32(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 __device__ __forceinline__ float4 rt32(float4 v) { return make_float4(rt32(v.x), rt32(v.y), rt32(v.z), rt32(v.w)); }
 }  // namespace vrwkv
+
+// ---- bf16 operand tiles (round 2): 64 rows x 64 bf16 = 8 KB, SWIZZLE_128B.  The same bytes serve as a K-major operand
+// (row = M/N index, the 64 columns = K) and as an MN-major operand (row = K line, the 64 columns = M/N): only the
+// instruction descriptor's major bit and the descriptor's K-step differ.  TMA boxes of [64 rows][64 bf16] loaded with
+// CU_TENSOR_MAP_SWIZZLE_128B land in exactly this layout.
+namespace vrwkv {
+constexpr uint32_t BT_BYTES = 8192;  // one bf16 tile
+__device__ __forceinline__ uint32_t bt_off(int row, int col) {  // byte offset of element (row, col)
+    return (uint32_t)row * 128u + ((((uint32_t)col >> 3) ^ ((uint32_t)row & 7u)) << 4) + ((uint32_t)col & 7u) * 2u;
+}
+// descriptors from b4 = (1024-aligned struct base) >> 4 and a byte offset (cheap: one add per descriptor)
+__device__ __forceinline__ uint64_t bdesc_k(uint32_t b4, uint32_t off_bytes) {  // K-major; K-step of 16 elements = +32 bytes
+    return ((uint64_t)(64u | (1u << 14) | (2u << 29)) << 32) | (uint64_t)(b4 + (off_bytes >> 4) + (1u << 16));
+}
+// MN-major; K-step of 16 K-lines = +2048 bytes; `lbo` = byte distance between consecutive 64-wide M/N blocks
+__device__ __forceinline__ uint64_t bdesc_mn(uint32_t b4, uint32_t off_bytes, uint32_t lbo = BT_BYTES) {
+    return ((uint64_t)(64u | (1u << 14) | (2u << 29)) << 32) | (uint64_t)(b4 + (off_bytes >> 4) + ((lbo >> 4) << 16));
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_mj(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+// A operand from TMEM (bf16 pairs packed in 32-bit columns: column c holds K elements 2c, 2c+1), B from shared memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_c),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 3-way bf16 split of an fp32 value: x = s0 + s1 + s2 to within 2^-25 |x| (each part round-to-nearest)
+__device__ __forceinline__ void split3(float x, uint16_t& s0, uint16_t& s1, uint16_t& s2) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(h0);
+    const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(h1);
+    s0 = __bfloat16_as_ushort(h0); s1 = __bfloat16_as_ushort(h1); s2 = __bfloat16_as_ushort(__float2bfloat16_rn(r2));
+}
+// the same for a pair (packed cvt): p0/p1/p2 hold {lo: x, hi: y}
+__device__ __forceinline__ void split3x2(float x, float y, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p0) : "f"(y), "f"(x));
+    const float rx = x - __uint_as_float(p0 << 16), ry = y - __uint_as_float(p0 & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(ry), "f"(rx));
+    const float qx = rx - __uint_as_float(p1 << 16), qy = ry - __uint_as_float(p1 & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(qy), "f"(qx));
+}
+}  // namespace vrwkv

@@ -17,6 +17,8 @@
 #include "wkv7_chunk_dstate.cuh"
 #include "wkv7_chunk_bwd.cuh"
 #include "wkv7_fwd2.cuh"
+#include "wkv7_x6_fwd.cuh"
+#include "wkv7_x6_bwd.cuh"
 
 using namespace vrwkv;
 
@@ -150,6 +152,74 @@ static int ensure_pool_keeps_memory() {
     return VRWKV_OK;
 }
 
+static int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+    }
+    return n;
+}
+
+static int make_tile_map(CUtensorMap* m, const void* base, int B, int T, int H) {  // [64 steps][64 channels] bf16 boxes, SWIZZLE_128B
+    return vrwkv_encode_2d(m, base, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)H * WKV_N, (uint64_t)B * T,
+                           (uint64_t)H * WKV_N * 2, WKV_N, X6_L, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+// round-2 forward: chunk-parallel persistent kernel, x6 products (wkv7_x6_fwd.cuh)
+static int launch_x6_fwd(const void* const* in, const Wkv7FwdArgs& a, bool chunk_ck, cudaStream_t st) {
+    int rc = ensure_pool_keeps_memory();
+    if (rc) return rc;
+    CUtensorMap tm[6];
+    for (int i = 0; i < 6; i++)
+        if ((rc = make_tile_map(&tm[i], in[i], a.B, a.T, a.H))) return rc;
+    const int BH = a.B * a.H, nitems = BH * (a.T / X6_L);
+    const size_t sync_bytes = ((size_t)(BH + 1) * sizeof(int) + 255) & ~(size_t)255;
+    const size_t chain_bytes = a.s ? 0 : (size_t)BH * 2 * WKV_N * WKV_N * sizeof(float);
+    uint8_t* ws = nullptr;
+    VRWKV_CUDA(cudaMallocAsync((void**)&ws, sync_bytes + chain_bytes, st));
+    VRWKV_CUDA(cudaMemsetAsync(ws, 0, sync_bytes, st));
+    X6FwdArgs xa{a.B, a.T, a.H, a.y, a.s, a.sa, a.state_in, a.state_out, chain_bytes ? (float*)(ws + sync_bytes) : nullptr, (int*)ws};
+    const size_t smem = sizeof(X6FwdSmem) + 1024;
+    auto kern = chunk_ck ? wkv7_x6_fwd_kernel<false> : wkv7_x6_fwd_kernel<true>;
+    VRWKV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = nitems < sm_count() ? nitems : sm_count();
+    kern<<<grid, X6_THREADS, smem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], xa);
+    VRWKV_CUDA(cudaGetLastError());
+    vrwkv_count_launch(1);
+    VRWKV_CUDA(cudaFreeAsync(ws, st));
+    return VRWKV_OK;
+}
+
+// round-2 backward: one chunk-parallel persistent kernel, x3 products (wkv7_x6_bwd.cuh)
+static int launch_x3_bwd(const uint16_t* w, const uint16_t* q, const uint16_t* k, const uint16_t* v, const uint16_t* a,
+                         const uint16_t* b, const uint16_t* dy, const float* sa, const Wkv7BwdArgs& args, int ck_per_chunk,
+                         cudaStream_t st) {
+    int rc = ensure_pool_keeps_memory();
+    if (rc) return rc;
+    const int B = args.B, T = args.T, H = args.H;
+    CUtensorMap tm[7];
+    const void* in[7] = {w, q, k, v, a, b, dy};
+    for (int i = 0; i < 7; i++)
+        if ((rc = make_tile_map(&tm[i], in[i], B, T, H))) return rc;
+    const int BH = B * H, nitems = BH * (T / X6_L);
+    const size_t sync_bytes = ((size_t)(BH + 1) * sizeof(int) + 255) & ~(size_t)255;
+    const size_t ring_bytes = (size_t)BH * 2 * WKV_N * WKV_N * sizeof(float);
+    uint8_t* ws = nullptr;
+    VRWKV_CUDA(cudaMallocAsync((void**)&ws, sync_bytes + ring_bytes, st));
+    VRWKV_CUDA(cudaMemsetAsync(ws, 0, sync_bytes, st));
+    X3BwdArgs xa{B, T, H, w, q, k, a, b, sa, args.s, ck_per_chunk, (float*)(ws + sync_bytes), (int*)ws,
+                 args.dw, args.dq, args.dk, args.dv, args.da, args.db};
+    const size_t smem = sizeof(X3BwdSmem) + 1024;
+    VRWKV_CUDA(cudaFuncSetAttribute(wkv7_x3_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = nitems < sm_count() ? nitems : sm_count();
+    wkv7_x3_bwd_kernel<<<grid, X6_THREADS, smem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], xa);
+    VRWKV_CUDA(cudaGetLastError());
+    vrwkv_count_launch(1);
+    VRWKV_CUDA(cudaFreeAsync(ws, st));
+    return VRWKV_OK;
+}
+
 // backward entirely on the tensor cores: dS boundary scan, then one CTA per (batch, head, chunk)
 static int launch_bwd_chunked(const uint16_t* w, const uint16_t* q, const uint16_t* k, const uint16_t* v, const uint16_t* a,
                               const uint16_t* b, const uint16_t* dy, const float* sa, const Wkv7BwdArgs& args, int ck_per_chunk,
@@ -225,15 +295,16 @@ extern "C" int vrwkv_wkv7_forward_ex(int B, int T, int H, const uint16_t* w, con
     Wkv7FwdArgs args{B, T, H, y, s, sa, state_in, state_out};
     cudaStream_t st = (cudaStream_t)stream;
     int var = g_fwd_variant.load();
-    if (var == 0) var = ((flags | default_flags()) & VRWKV_WKV7_BOUNDED_DECAY) ? 3 : 1;
+    if (var == 0) var = ((flags | default_flags()) & VRWKV_WKV7_BOUNDED_DECAY) ? ((flags & VRWKV_WKV7_TF32) ? 3 : 6) : 1;
     if (flags & VRWKV_WKV7_CHUNK_CHECKPOINTS) {
         if (!(flags & VRWKV_WKV7_BOUNDED_DECAY) || (T % CK_L) != 0 || state_in || state_out)
             return vrwkv_fail(VRWKV_EINVAL, "wkv7 forward: CHUNK_CHECKPOINTS needs BOUNDED_DECAY, T %% 64 == 0 and no carried state");
-        var = 3;
+        if (var != 6 && var != 3) var = 6;
     }
-    if (var == 3 && (T % CK_L) != 0) var = 1;  // the chunked kernel walks 64 steps at a time
+    if ((var == 3 || var == 6) && (T % CK_L) != 0) var = 1;  // the chunked kernels walk 64 steps at a time
     switch (var) {
-        case 3: return launch_chunk_fwd(in, args, (flags & VRWKV_WKV7_CHUNK_CHECKPOINTS) != 0, st);  // tensor cores (bounded decay)
+        case 3: return launch_chunk_fwd(in, args, (flags & VRWKV_WKV7_CHUNK_CHECKPOINTS) != 0, st);  // round-1 TF32 tensor-core kernel
+        case 6: return launch_x6_fwd(in, args, (flags & VRWKV_WKV7_CHUNK_CHECKPOINTS) != 0, st);     // round-2 x6 chunk-parallel kernel
         case 1: return launch_fwd2<4, 4>(tm, args, st);  // 4 rows x 8 columns per thread, 4 compute warps
         case 2: return launch_fwd2<2, 4>(tm, args, st);  // 2 rows x 8 columns per thread, 8 compute warps
         default: return vrwkv_fail(VRWKV_EINVAL, "wkv7 forward: unknown variant %d", var);
@@ -270,13 +341,20 @@ extern "C" int vrwkv_wkv7_backward_ex(int B, int T, int H, const uint16_t* w, co
     Wkv7BwdArgs args{B, T, H, s, dw, dq, dk, dv, da, db};
     cudaStream_t st = (cudaStream_t)stream;
     int var = g_bwd_variant.load();
-    if (var == 0) var = ((flags | default_flags()) & VRWKV_WKV7_BOUNDED_DECAY) ? 5 : 1;
-    if (flags & VRWKV_WKV7_CHUNK_CHECKPOINTS) {
-        if (!(flags & VRWKV_WKV7_BOUNDED_DECAY) || (T % CK_L) != 0 || var != 5)
-            return vrwkv_fail(VRWKV_EINVAL, "wkv7 backward: CHUNK_CHECKPOINTS needs BOUNDED_DECAY, T %% 64 == 0 and the chunked kernel");
+    // default with bounded decay: the step-by-step kernel unless the caller kept chunk-granularity checkpoints (then the
+    // chunked kernels are the only ones that can read them)
+    if (var == 0) {
+        if (!((flags | default_flags()) & VRWKV_WKV7_BOUNDED_DECAY)) var = 1;
+        else if (flags & VRWKV_WKV7_TF32) var = 5;
+        else var = (flags & VRWKV_WKV7_CHUNK_CHECKPOINTS) ? 7 : 1;
     }
-    if ((var == 3 || var == 4 || var == 5) && (T % CK_L) != 0) var = 1;
+    if (flags & VRWKV_WKV7_CHUNK_CHECKPOINTS) {
+        if (!(flags & VRWKV_WKV7_BOUNDED_DECAY) || (T % CK_L) != 0 || (var != 5 && var != 7))
+            return vrwkv_fail(VRWKV_EINVAL, "wkv7 backward: CHUNK_CHECKPOINTS needs BOUNDED_DECAY, T %% 64 == 0 and a chunked kernel");
+    }
+    if ((var == 3 || var == 4 || var == 5 || var == 7) && (T % CK_L) != 0) var = 1;
     switch (var) {
+        case 7: return launch_x3_bwd(w, q, k, v, a, b, dy, sa, args, (flags & VRWKV_WKV7_CHUNK_CHECKPOINTS) ? 1 : CK_L / WKV_TC, st);
         case 5: return launch_bwd_chunked(w, q, k, v, a, b, dy, sa, args, (flags & VRWKV_WKV7_CHUNK_CHECKPOINTS) ? 1 : CK_L / WKV_TC, st);
         case 3: return launch_bwd_segmented<4, 3>(tm, w, q, a, b, dy, args, st);  // needs sum_chunk exp(w) < ~85
         case 4: return launch_bwd_segmented<2, 3>(tm, w, q, a, b, dy, args, st);  // same, 2 rows per thread (8 compute warps)

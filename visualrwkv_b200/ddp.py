@@ -50,35 +50,58 @@ class GradBucketReducer:
             off += p.numel()
         self.buckets.append((flat, ps))
 
+    def _rebind(self):
+        """p.grad must stay a view into its bucket: `optimizer.zero_grad(set_to_none=True)` or `p.grad = None`
+        would silently detach it (the all-reduce would then average stale zeros).  Re-attach, keeping any
+        gradient the detached tensor already holds."""
+        for flat, ps in self.buckets:
+            off = 0
+            for p in ps:
+                view = flat[off:off + p.numel()].view_as(p)
+                if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                    if p.grad is not None:
+                        view.copy_(p.grad)
+                    p.grad = view
+                off += p.numel()
+
     def reset(self):
-        """Call once per step before backward: zero the flat gradient buffers (grads are views)."""
+        """Call once per step before backward: zero the flat gradient buffers (grads are views into them)."""
         for bi, (flat, ps) in enumerate(self.buckets):
             flat.zero_()
             self._pending[bi] = len(ps)
+        self._rebind()
         self._handles = []
+        self._next = 0  # buckets are launched strictly in index order on every rank
+
+    def _launch(self, bi):
+        flat = self.buckets[bi][0]
+        if dist.get_backend(self.pg) == "nccl":
+            h = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.pg, async_op=True)
+            self._handles.append((h, None))
+        else:  # gloo (CPU tests): SUM then scale
+            h = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+            self._handles.append((h, flat))
 
     def _hook(self, p):
         bi = self._bucket_of[p]
+        if p.grad is None or p.grad.data_ptr() < self.buckets[bi][0].data_ptr() or \
+                p.grad.data_ptr() >= self.buckets[bi][0].data_ptr() + self.buckets[bi][0].numel() * p.element_size():
+            raise RuntimeError("GradBucketReducer: a parameter's .grad no longer points into its bucket "
+                               "(zero_grad(set_to_none=True)?); call reducer.reset() before every backward")
         self._pending[bi] -= 1
-        if self._pending[bi] == 0 and self.world > 1:
-            flat = self.buckets[bi][0]
-            if dist.get_backend(self.pg) == "nccl":
-                h = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.pg, async_op=True)
-                self._handles.append((h, None))
-            else:  # gloo (CPU tests): SUM then scale
-                h = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
-                self._handles.append((h, flat))
+        # launch every complete bucket at the head of the queue: the collective order is the bucket order on every rank,
+        # whatever order the hooks fire in (a bucket whose parameters got no gradient on this rank is launched in finish())
+        while self.world > 1 and self._next < len(self.buckets) and self._pending[self._next] == 0:
+            self._launch(self._next)
+            self._next += 1
 
     def finish(self):
-        """Call after backward, before the optimizer: waits for every in-flight bucket."""
+        """Call after backward, before the optimizer: launches what is left (same order on every rank) and waits."""
         if self.world > 1:
-            # parameters that received no gradient this step still have to be reduced
-            for bi, n in enumerate(self._pending):
-                if n > 0:
-                    flat = self.buckets[bi][0]
-                    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
-                    flat.div_(self.world)
-                    self._pending[bi] = 0
+            while self._next < len(self.buckets):
+                self._pending[self._next] = 0
+                self._launch(self._next)
+                self._next += 1
         for h, flat in self._handles:
             h.wait()
             if flat is not None:

@@ -12,6 +12,7 @@ backward and reduce per-channel parameter gradients from per-CTA fp32 partials.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -160,14 +161,33 @@ def relu_sq_backward_from_act(act, dy):
     return dx
 
 
+# Which WKV7 kernels the fused time-mix block runs (bench.py --wkv, env VRWKV_WKV_PATH).  The block builds
+# w = -softplus(.) - 0.5 itself (tmix_mid_fwd_kernel, model.py:176), so it may promise bounded decay.
+#   "x6"   : chunk-parallel tensor-core forward with bf16-split products (wkv7_x6_fwd.cuh) + the matching backward —
+#            fp32-level accuracy, passes the same element-wise parity asserts as the step-by-step kernels (default);
+#   "step" : the step-by-step fp32 kernels (wkv7_fwd2/bwd2.cuh), what torch.ops.wind_backstepping binds;
+#   "tf32" : the round-1 single-pass TF32 chunk kernels (faster products, sa/s only to ~5e-4: comparison only).
+WKV_PATH = os.environ.get("VRWKV_WKV_PATH", "x6")
+X3_BACKWARD = True   # the x3 chunked backward reads one checkpoint per 64-step chunk (a quarter of the checkpoint traffic)
+
+
+def set_wkv_path(path: str) -> None:
+    global WKV_PATH
+    assert path in ("x6", "step", "tf32"), path
+    WKV_PATH = path
+
+
 def wkv7_fwd_raw(w, q, k, v, a, b):
-    """[B,T,H,64] bf16 x6 -> y, s, sa.  The fused time-mix block builds w = -softplus(.) - 0.5 itself
-    (tmix_mid_fwd_kernel, model.py:176), so it may promise bounded decay (include/vrwkv_b200.h)."""
-    return _wkv7.forward_raw(w, q, k, v, a, b, bounded_decay=True, chunk_checkpoints=True)
+    """[B,T,H,64] bf16 x6 -> y, s, sa."""
+    if WKV_PATH == "tf32":
+        return _wkv7.forward_raw(w, q, k, v, a, b, bounded_decay=True, chunk_checkpoints=True, tf32=True)
+    if WKV_PATH == "x6":
+        return _wkv7.forward_raw(w, q, k, v, a, b, bounded_decay=True, chunk_checkpoints=X3_BACKWARD)
+    return _wkv7.forward_raw(w, q, k, v, a, b)
 
 
 def wkv7_bwd_raw(w, q, k, v, a, b, dy, s, sa):
-    return _wkv7.backward_raw(w, q, k, v, a, b, dy, s, sa, bounded_decay=True)  # dw, dq, dk, dv, da, db
+    return _wkv7.backward_raw(w, q, k, v, a, b, dy, s, sa, bounded_decay=(WKV_PATH != "step"), tf32=(WKV_PATH == "tf32"))
 
 
 # ------------------------------------------------------------------------------------------------------

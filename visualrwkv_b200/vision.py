@@ -7,6 +7,9 @@ reference discards, is not evaluated.
 """
 from __future__ import annotations
 
+import json
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -20,12 +23,45 @@ SIGLIP_CONFIGS = {
 }
 
 
+def _config_from_hf(d: dict) -> dict:
+    """HF config.json (SiglipVisionConfig, or the `vision_config` of a full SiglipConfig) -> our keys."""
+    d = d.get("vision_config", d)
+    return dict(hidden=int(d.get("hidden_size", 768)), layers=int(d.get("num_hidden_layers", 12)),
+                heads=int(d.get("num_attention_heads", 12)), mlp=int(d.get("intermediate_size", 3072)),
+                image=int(d.get("image_size", 224)), patch=int(d.get("patch_size", 16)),
+                eps=float(d.get("layer_norm_eps", 1e-6)))
+
+
 def resolve_config(name_or_path: str) -> dict:
-    key = name_or_path.rstrip("/").split("/")[-1]
+    """A checkpoint directory (config.json wins) or a known tower name.  Names match on their tail with `siglip2-`
+    folded onto `siglip-` (same architecture; the reference's scripts pass e.g. google/siglip2-base-patch16-256,
+    VisualRWKV-v7/v7.01/scripts)."""
+    cfg_json = os.path.join(name_or_path, "config.json")
+    if os.path.isfile(cfg_json):
+        with open(cfg_json) as f:
+            return _config_from_hf(json.load(f))
+    key = name_or_path.rstrip("/").split("/")[-1].replace("siglip2-", "siglip-")
     for k, v in SIGLIP_CONFIGS.items():
         if key.endswith(k):
             return dict(v)
-    raise ValueError(f"unknown SigLIP tower {name_or_path!r}; known: {sorted(SIGLIP_CONFIGS)}")
+    raise ValueError(f"unknown SigLIP tower {name_or_path!r}; known: {sorted(SIGLIP_CONFIGS)} or a directory with config.json")
+
+
+def _checkpoint_tensors(path: str) -> dict | None:
+    """Weights of a HF checkpoint directory (model.safetensors / sharded *.safetensors / pytorch_model.bin), or None."""
+    if not os.path.isdir(path):
+        return None
+    st = sorted(f for f in os.listdir(path) if f.endswith(".safetensors"))
+    if st:
+        from safetensors.torch import load_file
+        out = {}
+        for f in st:
+            out.update(load_file(os.path.join(path, f)))
+        return out
+    pt = os.path.join(path, "pytorch_model.bin")
+    if os.path.isfile(pt):
+        return torch.load(pt, map_location="cpu", weights_only=True)
+    return None
 
 
 class _Embeddings(nn.Module):
@@ -79,6 +115,24 @@ class SiglipVisionTower(nn.Module):
         self.cfg = resolve_config(name_or_path)
         self.embed_dim = self.cfg["hidden"]
         self.vision_model = _VisionModel(self.cfg)
+        # the reference calls SiglipVisionModel.from_pretrained(vision_tower_path) (v7.01/src/model.py:347-350): when the
+        # path is a checkpoint directory its weights are loaded; a bare name (no files offline) keeps the random init
+        tensors = _checkpoint_tensors(name_or_path)
+        self.pretrained = tensors is not None
+        if tensors is not None:
+            self.load_state_dict(tensors)
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        """Accepts HF SiglipVisionModel / SiglipModel checkpoints: the attention-pooling head (`vision_model.head.*`,
+        whose output the reference discards) and the text tower are dropped before the strict check."""
+        sd = {}
+        for k, v in state_dict.items():
+            if k.startswith("text_model.") or k in ("logit_scale", "logit_bias"):
+                continue
+            if ".head." in k and k.split(".head.")[0].endswith("vision_model"):
+                continue
+            sd[k] = v
+        return super().load_state_dict(sd, strict=strict, assign=assign)
 
     @torch.no_grad()
     def forward(self, pixels):

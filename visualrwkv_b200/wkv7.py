@@ -40,14 +40,16 @@ def launch_count() -> int:
 
 BOUNDED_DECAY = 1      # include/vrwkv_b200.h: VRWKV_WKV7_BOUNDED_DECAY
 CHUNK_CHECKPOINTS = 2  # VRWKV_WKV7_CHUNK_CHECKPOINTS
+TF32 = 4               # VRWKV_WKV7_TF32 (round-1 kernels; outside the north-star tolerance)
 CHUNK = 64
 
 
-def _flags(bounded_decay, chunk_checkpoints):
-    return ctypes.c_uint((BOUNDED_DECAY if bounded_decay else 0) | (CHUNK_CHECKPOINTS if chunk_checkpoints else 0))
+def _flags(bounded_decay, chunk_checkpoints, tf32=False):
+    return ctypes.c_uint((BOUNDED_DECAY if bounded_decay else 0) | (CHUNK_CHECKPOINTS if chunk_checkpoints else 0) |
+                         (TF32 if (tf32 and bounded_decay) else 0))
 
 
-def forward_raw(w, q, k, v, a, b, bounded_decay: bool = False, chunk_checkpoints: bool = False):
+def forward_raw(w, q, k, v, a, b, bounded_decay: bool = False, chunk_checkpoints: bool = False, tf32: bool = False):
     """[B,T,H,64] bf16 x6 (kernel order) -> y, s, sa through the C ABI (vrwkv_wkv7_forward_ex).
 
     bounded_decay=True is the caller's promise that exp(w) <= 0.607 (RWKV-7's w = -softplus(.) - 0.5, model.py:176);
@@ -66,14 +68,14 @@ def forward_raw(w, q, k, v, a, b, bounded_decay: bool = False, chunk_checkpoints
         with torch.cuda.device(w.device):
             rc = L.vrwkv_wkv7_forward_ex(B, T, H, _lib.ptr(w), _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(a),
                                          _lib.ptr(b), _lib.ptr(y), _lib.ptr(s), _lib.ptr(sa), None, None,
-                                         _flags(bounded_decay, chunk_checkpoints), _lib.cur_stream())
+                                         _flags(bounded_decay, chunk_checkpoints, tf32), _lib.cur_stream())
         _lib.check(rc, "vrwkv_wkv7_forward_ex")
 
     _timed("fwd", run)
     return y, s, sa
 
 
-def backward_raw(w, q, k, v, a, b, dy, s, sa, bounded_decay: bool = False):
+def backward_raw(w, q, k, v, a, b, dy, s, sa, bounded_decay: bool = False, tf32: bool = False):
     """Returns dw, dq, dk, dv, da, db (bf16 [B,T,H,64]) through vrwkv_wkv7_backward_ex (the checkpoint granularity is
     read off the shape of s)."""
     L = _lib.lib()
@@ -87,7 +89,7 @@ def backward_raw(w, q, k, v, a, b, dy, s, sa, bounded_decay: bool = False):
             rc = L.vrwkv_wkv7_backward_ex(B, T, H, _lib.ptr(w), _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(a),
                                           _lib.ptr(b), _lib.ptr(dy), _lib.ptr(s), _lib.ptr(sa),
                                           *[_lib.ptr(o) for o in outs],
-                                          _flags(bounded_decay, chunk_checkpoints), _lib.cur_stream())
+                                          _flags(bounded_decay, chunk_checkpoints, tf32), _lib.cur_stream())
         _lib.check(rc, "vrwkv_wkv7_backward_ex")
 
     _timed("bwd", run)
