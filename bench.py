@@ -33,9 +33,22 @@ import torch  # noqa: E402
 
 WKV_FWD_BYTES_PER_ELEM = 14  # 6 bf16 reads + 1 bf16 write
 WKV_BWD_BYTES_PER_ELEM = 26  # 7 bf16 reads + 6 bf16 writes
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at cfg2 (B8 T2048 C768), ncu --set full, profiles/r1e_*:
-NCU_TRAFFIC_FWD = int((151.359 + 83.432) * 1e6)                       # wkv7_chunk_fwd_kernel<chunk checkpoints> (y 25 + sa 50 + s 50 MB of writes)
-NCU_TRAFFIC_BWD = int((121.974 + 22.821 + 324.469 + 168.727) * 1e6)   # dstate scan + chunk-local backward (incl. 50 MB G scratch)
+# The WKV7 kernels behind each --wkv path, and dram__bytes_read.sum + dram__bytes_write.sum per launch at cfg2
+# (B8 T2048 C768) from the ncu --set full captures named beside them (profiles/); None = not captured for this build.
+WKV_PATHS = {
+    "x6": {"fwd": "wkv7_x6_fwd_kernel<chunk checkpoints>", "bwd": "wkv7_x3_bwd_kernel",
+           "traffic_fwd": int((151.093 + 84.057) * 1e6), "traffic_bwd": None, "ncu": "profiles/r2_wkv7_x6_summary.csv"},
+    "step": {"fwd": "wkv7_fwd2_kernel<4,4>", "bwd": "wkv7_bwd2_kernel<4,3>", "traffic_fwd": int((151 + 226) * 1e6), "traffic_bwd": None,
+             "ncu": "profiles/r1b_*"},
+    "tf32": {"fwd": "wkv7_chunk_fwd_kernel<chunk checkpoints>", "bwd": "wkv7_chunk_dstate_kernel + wkv7_chunk_bwd_kernel",
+             "traffic_fwd": int((151.359 + 83.432) * 1e6), "traffic_bwd": int((121.974 + 22.821 + 324.469 + 168.727) * 1e6),
+             "ncu": "profiles/r1e_wkv7_tc_model_path_summary.csv"},
+}
+CONFIGS = {   # BASELINE.json configs[1] and configs[2] (one GPU's share)
+    "cfg2": dict(layers=12, embd=768, batch=8, ctx=2048, name="RWKV-x070 0.1B (L12 C768 H12 N64)"),
+    "cfg3": dict(layers=24, embd=2048, batch=4, ctx=2048, name="RWKV-x070 1.5B (L24 C2048 H32 N64)"),
+}
+LORA_RANKS = {768: 64 + 64 + 32 + 128, 2048: 96 + 96 + 64 + 256}   # v7.00/src/model.py:118,127,133,140 (w, a, v, g)
 
 
 def load_peaks():
@@ -50,9 +63,9 @@ def load_peaks():
 # --------------------------------------------------------------------------------------------------
 # CPU baseline (oracle port) — shared by cpu_baseline and --impl reference
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps: int, warmup: int, T: int = 128, B: int = 1, n_img_tok: int = 36):
-    """fp32 restatement of the same model (0.1B + SigLIP-B/16@224) on the host cores, fwd+bwd, on a bounded
-    sample: B x T tokens with n_img_tok image tokens (196 patches pooled to n_img_tok)."""
+def cpu_reference_run(steps: int, warmup: int, T: int = 512, B: int = 1, n_img_tok: int = 196):
+    """fp32 restatement of the same model (0.1B + SigLIP-B/16@224) on the host cores, fwd+bwd, on BASELINE.json
+    configs[0]: one 224x224 image (196 patch tokens, identity pooling), ctx 512, batch 1."""
     from oracle import model_ref as MR
     from visualrwkv_b200.model import VisualRWKV, default_args, randomize_zero_init
     # small-operator workload: beyond ~32 threads the fork/join cost of every op outweighs the parallelism (on the
@@ -99,6 +112,34 @@ def cpu_reference_run(steps: int, warmup: int, T: int = 128, B: int = 1, n_img_t
             "ms_per_step": dt * 1e3}
 
 
+def ref_kernel_times(B, T, H, dev):
+    """ms per launch of the reference forward_kernel / backward_kernel (wkv7_cuda.cu) on (B,T,H,64) realistic inputs;
+    None when oracle/_ref was not built (no /root/reference at build time)."""
+    try:
+        from oracle import ref_kernel as RK
+        from oracle import wkv7 as O
+        if not RK.available():
+            return None
+        inp = [x.to(dev) for x in O.make_inputs(B, T, H, 64, seed=42)]
+        out = {}
+        for name, fn in (("fwd", lambda: RK.forward(*inp[:6])), ("bwd", None)):
+            if name == "bwd":
+                _, rs, rsa = RK.forward(*inp[:6])
+                fn = lambda: RK.backward(*inp, rs, rsa)  # noqa: E731
+            for _ in range(2):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            out[name] = e0.elapsed_time(e1) / 5
+        return out
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)[:200]}
+
+
 # --------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -106,28 +147,38 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="per-GPU batch (config: 8)")
-    ap.add_argument("--ctx", type=int, default=2048)
-    ap.add_argument("--layers", type=int, default=12)
-    ap.add_argument("--embd", type=int, default=768)
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS), help="BASELINE.json configs[1] (headline) or configs[2]")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the config's)")
+    ap.add_argument("--ctx", type=int, default=None)
+    ap.add_argument("--layers", type=int, default=None)
+    ap.add_argument("--embd", type=int, default=None)
+    ap.add_argument("--wkv", default="x6", choices=sorted(WKV_PATHS),
+                    help="WKV7 kernels of the time-mix block: x6 (default; chunked tensor-core kernels at fp32-level accuracy, pass the "
+                         "strict parity tests), step (step-by-step fp32 kernels), tf32 (round-1 kernels, outside the tolerance)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-kernel", action="store_true")
     ap.add_argument("--grad-cp", type=int, default=0)
     a = ap.parse_args()
+    cfg = CONFIGS[a.config]
+    for k_ in ("batch", "ctx", "layers", "embd"):
+        if getattr(a, k_) is None:
+            setattr(a, k_, cfg[k_])
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    config = {"workload": "RWKV-x070 0.1B (L12 C768 H12 N64) + SigLIP-B/16@224 (196 patches -> AdaptiveAvgPool -> 576 image tokens), "
-                          "ctx 2048, batch 8/GPU, fwd+bwd+allreduce+AdamW",
-              "global_batch": a.batch * world, "seq_len": a.ctx, "image_tokens": 576, "parallelism": f"dp{world}",
+    config = {"workload": f"{cfg['name']} + SigLIP-B/16@224 (196 patches -> AdaptiveAvgPool -> 576 image tokens), "
+                          f"ctx {a.ctx}, batch {a.batch}/GPU, fwd+bwd+allreduce+AdamW; WKV7 path: {a.wkv}",
+              "global_batch": a.batch * world, "seq_len": a.ctx, "image_tokens": 576, "parallelism": f"dp{world}", "wkv": a.wkv,
               "l2": "working set per step (>2 GB of activations) exceeds the 126 MB L2; no explicit flush"}
 
     if a.impl == "reference":
         if rank != 0:
             return
-        r = cpu_reference_run(a.steps, a.warmup)
+        r = cpu_reference_run(max(a.steps, 5), a.warmup)
+        config["reference_sample"] = r["sample"]   # what one timed step of this arm actually is (a bounded sample of the workload)
         line = {"impl": "reference", "metric": "tokens/s fwd+bwd (T=2048, 576 img-tok)", "value": r["value"], "unit": "tokens/s",
-                "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"],
+                "n_gpus": a.gpus, "steps": max(a.steps, 5), "warmup": a.warmup, "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config, "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu")},
                 "e2e": {"value": r["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -142,7 +193,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from visualrwkv_b200 import _lib, wkv7
+    from visualrwkv_b200 import _lib, fused, wkv7
+    fused.set_wkv_path(a.wkv)
     from visualrwkv_b200.benchutil import ClockSampler
     from visualrwkv_b200.ddp import GradBucketReducer
     from visualrwkv_b200.model import VisualRWKV, default_args, randomize_zero_init
@@ -237,24 +289,34 @@ def main():
             fms, bms = sum(fwd) / len(fwd), sum(bwd) / len(bwd)
             peak = peaks["hbm_gbs"]
             # DRAM bytes per launch from the ncu --set full capture of this configuration (profiles/r1e_wkv7_tc_model_path_summary.csv)
-            line["roofline"] = {"kernel": "wkv7 backward = wkv7_chunk_dstate_kernel + wkv7_chunk_bwd_kernel", "bound": "hbm", "achieved": WKV_BWD_BYTES_PER_ELEM * nel / bms / 1e6,
+            wp = WKV_PATHS[a.wkv]
+            at_cfg2 = (B, T, args.n_embd) == (8, 2048, 768)
+            line["roofline"] = {"kernel": "wkv7 backward = " + wp["bwd"], "bound": "hbm", "achieved": WKV_BWD_BYTES_PER_ELEM * nel / bms / 1e6,
                                 "peak": peak, "unit": "GB/s", "frac": WKV_BWD_BYTES_PER_ELEM * nel / bms / 1e6 / peak,
-                                "traffic": NCU_TRAFFIC_BWD if (B, T, args.n_embd) == (8, 2048, 768) else None, "traffic_unit": "bytes",
+                                "traffic": wp["traffic_bwd"] if at_cfg2 else None, "traffic_unit": "bytes", "traffic_source": wp["ncu"],
                                 "avg_launch_ms": bms, "launches_timed": len(bwd),
                                 "peak_source": peaks["source"], "share_of_step": sum(bwd) / a.steps / ms}
-            line["roofline_wkv7_fwd"] = {"kernel": "wkv7_chunk_fwd_kernel", "bound": "hbm", "achieved": WKV_FWD_BYTES_PER_ELEM * nel / fms / 1e6,
+            line["roofline_wkv7_fwd"] = {"kernel": wp["fwd"], "bound": "hbm", "achieved": WKV_FWD_BYTES_PER_ELEM * nel / fms / 1e6,
                                          "peak": peak, "unit": "GB/s", "frac": WKV_FWD_BYTES_PER_ELEM * nel / fms / 1e6 / peak,
-                                         "traffic": NCU_TRAFFIC_FWD if (B, T, args.n_embd) == (8, 2048, 768) else None,
+                                         "traffic": wp["traffic_fwd"] if at_cfg2 else None,
                                          "traffic_unit": "bytes", "avg_launch_ms": fms, "launches_timed": len(fwd),
                                          "share_of_step": sum(fwd) / a.steps / ms}
         # model FLOPs (GEMMs only): fwd 281 MFLOP/token at 0.1B -> x3 for fwd+bwd
         C, L, V = args.n_embd, args.n_layer, args.vocab_size
-        lora = 64 + 64 + 32 + 128 if C == 768 else 0
+        lora = LORA_RANKS.get(C, 0)
         per_tok = L * (8 * C * C + 4 * C * lora + 16 * C * C) + 2 * C * V
         line["gemm_tflops_achieved"] = 3 * per_tok * B * T / (ms / 1e3) / 1e12
         line["gemm_frac_of_bf16_peak"] = line["gemm_tflops_achieved"] / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"])
+        if world == 1 and not a.no_ref_kernel:
+            # the reference's own WKV7 kernel (oracle/_ref, compiled from the mounted sources) on the same GPU and inputs,
+            # outside the timed region: makes the "x reference kernel" figures driver-observable
+            rk = ref_kernel_times(B, T, args.dim_att // 64, dev)
+            if rk is not None:
+                line["ref_kernel_ms"] = rk
+                if fwd and bwd:
+                    line["wkv7_speedup_vs_ref_kernel"] = {"fwd": rk["fwd"] / fms, "bwd": rk["bwd"] / bms}
         if world == 1 and not a.no_cpu_baseline:
-            r = cpu_reference_run(steps=2, warmup=1)
+            r = cpu_reference_run(steps=3, warmup=1)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu")}
         print(json.dumps(line))
     if world > 1:

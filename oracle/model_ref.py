@@ -74,6 +74,11 @@ class _RefKernelWKV(torch.autograd.Function):
         return RK.backward(w, q, k, v, a, b, dy.contiguous(), s, sa)
 
 
+def ref_kernel_available() -> bool:
+    from oracle import ref_kernel as RK
+    return torch.cuda.is_available() and RK.available()
+
+
 def ref_kernel_wkv(r, w, k, v, a, b):
     """The unmodified reference CUDA kernel (oracle/_ref) behind the RUN_CUDA_RWKV7g signature."""
     B, T, HC = r.shape

@@ -35,11 +35,18 @@ def _rel(a, b):
 
 
 def _ours_wkv(r, w, k, v, a, b):
+    """WKV7 inside the eager reference graph of the BLOCK tests.  When oracle/_ref is present this is the unmodified
+    reference kernel; otherwise our own op — which is pinned separately, kernel by kernel, in tests/test_wkv7_gpu.py,
+    so the block tests then check everything around it."""
+    if MR.ref_kernel_available():
+        return MR.ref_kernel_wkv(r, w, k, v, a, b)
     from visualrwkv_b200.wkv7 import RUN_CUDA_RWKV7g
     return RUN_CUDA_RWKV7g(*[t.contiguous() for t in (r, w, k, v, a, b)])
 
 
-@pytest.mark.parametrize("n_embd,B,T", [(128, 2, 64), (768, 1, 48)])
+# (768, 1, 2048): BASELINE cfg2 width and context — T % 64 == 0, so the blocks really take the chunked x6/x3 WKV7 kernels
+# (T = 48 falls back to the step-by-step kernels: wkv7_host.cu)
+@pytest.mark.parametrize("n_embd,B,T", [(128, 2, 64), (768, 1, 48), (768, 1, 2048)])
 def test_blocks_vs_bf16_eager_reference(n_embd, B, T):
     m, args = _mk(n_embd, 2)
     H = n_embd // 64
@@ -143,3 +150,23 @@ def test_no_cpu_fallback():
     m = RWKV(args)
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 16, 128))
+
+
+def test_token_shift_mix_is_bit_exact():
+    """north star: "bit-exact for token-shift index/gather".  The mix-only path of ln_mix_forward (no LayerNorm) against
+    the eager bf16 graph of model.py:149,166-173: xx = shift(x) - x ; x + xx * c — every output bit, including the t = 0
+    row of every sequence in the batch (shift wraps to zero there, never to the previous sequence's last row)."""
+    from visualrwkv_b200 import fused
+    torch.manual_seed(11)
+    for (B, T, C) in [(3, 16, 128), (2, 100, 768), (4, 64, 2048)]:
+        x = torch.randn(B, T, C, device="cuda").to(torch.bfloat16)
+        coefs = [torch.rand(C, device="cuda").to(torch.bfloat16) for _ in range(6)]
+        outs, _, _ = fused.ln_mix_forward(x.view(B * T, C), T, None, None, 1e-5, coefs)
+        xx = torch.cat([torch.zeros_like(x[:, :1]), x[:, :-1]], dim=1) - x
+        for o, c in zip(outs, coefs):
+            ref = x + xx * c.view(1, 1, C)
+            assert torch.equal(o.view(B, T, C), ref)
+        # the gather itself: with c = 1 the mixed stream is x + (shift(x) - x), whose t = 0 rows are x + (0 - x)
+        one = torch.ones(C, device="cuda", dtype=torch.bfloat16)
+        (o1,), _, _ = fused.ln_mix_forward(x.view(B * T, C), T, None, None, 1e-5, [one])
+        assert torch.equal(o1.view(B, T, C)[:, 0], x[:, 0] + (torch.zeros_like(x[:, 0]) - x[:, 0]))

@@ -151,4 +151,4 @@ def test_bench_line_keys():
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] == 4
     r = d["roofline"]
     assert r["bound"] == "hbm" and 0 < r["frac"] < 1 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
-    assert "chunk" in r["kernel"]  # the model path promises bounded decay: tensor-core kernels
+    assert "x3_bwd" in r["kernel"] and d["config"]["wkv"] == "x6"  # default: the chunked kernels that pass the strict parity tests

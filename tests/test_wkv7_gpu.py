@@ -156,60 +156,110 @@ def test_error_behaviour(ops):
 
 
 # ------------------------------------------------------------------------------------------------------
-# Chunked tensor-core path (VRWKV_WKV7_BOUNDED_DECAY): TF32 operands, fp32 accumulation.  Tolerances: the bf16
-# outputs stay dominated by their own rounding (1.65e-3 RMS); the fp32 side outputs (sa, s) carry the TF32 operand
-# rounding (2^-11 = 4.9e-4 per operand) — oracle/wkv7_chunked.py with tf32_round predicts 4-6e-4.
+# Chunked tensor-core path, round 2 (VRWKV_WKV7_BOUNDED_DECAY): x6 forward / x3 backward (bf16-split products).
+# It carries the benchmark, so it is held to EXACTLY the asserts of the step-by-step path above: rtol 1e-3 / atol 1e-5
+# element-wise on the fp32 outputs sa and s, >= 99.5 % of y within one bf16 ulp (bit-identical to the reference kernel's
+# output on the goldens), gradients no worse than 1.02x the reference kernel's own error.
 # ------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("bwd_variant", [5, 3], ids=["chunked-bwd", "segmented-bwd"])
-@pytest.mark.parametrize("shape,kind,seed", [((1, 64, 1), "realistic", 3), ((2, 512, 3), "realistic", 5),
-                                               ((1, 2048, 2), "realistic", 6), ((2, 256, 2), "stress", 8)])
-def test_chunked_forward_and_tensor_core_backward_vs_fp64_oracle(shape, kind, seed, bwd_variant):
-    """bwd_variant 5 (default with bounded decay): dS scan + chunk-local tensor-core kernel; 3: dS scan + the
-    step-by-step kernel on 64-step segments."""
+def run_x6(inp, ck64):
     from visualrwkv_b200 import wkv7 as W
+    w, q, k, v, a, b, dy = inp
+    y, s, sa = W.forward_raw(w, q, k, v, a, b, bounded_decay=True, chunk_checkpoints=ck64)
+    g = W.backward_raw(w, q, k, v, a, b, dy, s, sa, bounded_decay=True)
+    torch.cuda.synchronize()
+    W.domain_check()
+    return y, s, sa, g
+
+
+@pytest.mark.parametrize("ck64", [False, True], ids=["ck16", "ck64"])
+@pytest.mark.parametrize("shape,kind,seed", [((2, 64, 3), "realistic", 7), ((1, 64, 1), "realistic", 3), ((3, 256, 5), "realistic", 2),
+                                               ((2, 512, 3), "realistic", 5), ((1, 2048, 2), "realistic", 6),
+                                               ((2, 256, 2), "stress", 8), ((1, 1024, 2), "stress", 4)])
+def test_x6_parity_vs_fp64_oracle(shape, kind, seed, ck64):
     B, T, H = shape
     cpu = O.make_inputs(B, T, H, 64, seed=seed, kind=kind)
-    w, q, k, v, a, b, dy = [x.cuda() for x in cpu]
-    y, s, sa = W.forward_raw(w, q, k, v, a, b, bounded_decay=True)
-    W.set_variant(0, bwd_variant)
-    try:
-        g = W.backward_raw(w, q, k, v, a, b, dy, s, sa, bounded_decay=True)
-    finally:
-        W.set_variant(0, 0)
-    W.domain_check()
+    y, s, sa, g = run_x6([x.cuda() for x in cpu], ck64)
     y64, s64, sa64 = O.forward(*cpu[:6])
-    assert O.err_ratio(y.float().cpu().numpy(), y64) < 2.2e-3
-    assert O.err_ratio(sa.cpu().numpy(), sa64) < 1.2e-3
-    assert O.err_ratio(s.cpu().numpy(), s64) < 1.2e-3
+    np.testing.assert_allclose(sa.cpu().numpy(), sa64, rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(s.cpu().numpy(), s64[:, :, 3::4] if ck64 else s64, rtol=1e-3, atol=1e-5)
+    assert O.err_ratio(y.float().cpu().numpy(), y64) < 2.0e-3
+    assert (O.bf16_ulp_diff(y.float().cpu().numpy(), O.to_bf16_f32(y64)) <= 1).mean() > 0.995
     g64 = O.backward(*cpu, s64, sa64)
-    # realistic inputs (a = -kk, b = kk*gate: contractive transitions): within 1.5x of the bf16 output rounding.
-    # The stress set draws a, b ~ U(-1,1) (|a.b| ~ 4.6 per step); dw there is a sum with heavy cancellation and shows
-    # the TF32 rounding of the chunk-boundary dS values (3.3e-3 measured) — still a relative error, bounded here.
-    tol = 2.4e-3 if kind == "realistic" else 4.5e-3
     for n, x, r in zip(NAMES, g, g64):
-        assert O.err_ratio(x.float().cpu().numpy(), r) < tol, n
+        assert O.err_ratio(x.float().cpu().numpy(), r) < 2.0e-3, n
 
 
-def test_chunked_path_matches_step_kernels_closely():
-    """Same inputs through both paths: y differs by at most a few bf16 ulps, gradients agree to ~1e-3 RMS."""
-    from visualrwkv_b200 import wkv7 as W
-    cpu = O.make_inputs(2, 256, 4, 64, seed=21)
-    w, q, k, v, a, b, dy = [x.cuda() for x in cpu]
-    y0, s0, sa0 = W.forward_raw(w, q, k, v, a, b)
-    g0 = W.backward_raw(w, q, k, v, a, b, dy, s0, sa0)
-    y1, s1, sa1 = W.forward_raw(w, q, k, v, a, b, bounded_decay=True)
-    g1 = W.backward_raw(w, q, k, v, a, b, dy, s1, sa1, bounded_decay=True)
-    d = (y0.float() - y1.float()).abs()
-    assert float(d.max()) <= 0.02 * float(y0.float().abs().max())          # a few bf16 ulps of the largest outputs
-    assert O.err_ratio(y1.float().cpu().numpy(), y0.float().cpu().numpy().astype(np.float64)) < 2.5e-3
-    for n, x0, x1 in zip(NAMES, g0, g1):
-        assert O.err_ratio(x1.float().cpu().numpy(), x0.float().cpu().numpy().astype(np.float64)) < 2.5e-3, n
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_x6_parity_vs_reference_goldens(path):
+    z = np.load(path)
+    B, T, H = int(z["B"]), int(z["T"]), int(z["H"])
+    if T % 64:
+        pytest.skip("the chunked kernels need T % 64 == 0 (the dispatcher falls back to the step-by-step kernels)")
+    cpu = O.make_inputs(B, T, H, 64, seed=int(z["seed"]), kind=str(z["kind"]))
+    y, s, sa, g = run_x6([x.cuda() for x in cpu], False)
+    bf = lambda name: torch.from_numpy(z[name]).view(torch.bfloat16).float().numpy()
+    np.testing.assert_allclose(sa.cpu().numpy(), z["sa"], rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(s[:, :, -1].cpu().numpy(), z["s_last"], rtol=1e-3, atol=1e-5)
+    yd = O.bf16_ulp_diff(y.float().cpu().numpy(), bf("y"))
+    assert (yd == 0).mean() > 0.995 and (yd <= 1).mean() > 0.9995
+    for n, x in zip(NAMES, g):
+        xa, ra = x.float().cpu().numpy(), bf(n)
+        ok = (O.bf16_ulp_diff(xa, ra) <= 1) | (np.abs(xa - ra) <= 1e-3 * np.sqrt(np.mean(ra ** 2)))
+        assert ok.mean() > 0.999, n
+        assert O.err_ratio(xa, ra) < 1e-3, n
 
 
-def test_chunked_forward_state_chaining_is_exact():
+def test_x6_not_worse_than_reference_kernel():
+    from oracle import ref_kernel as RK
+    if not RK.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    cpu = O.make_inputs(2, 512, 4, 64, seed=3)
+    inp = [x.cuda() for x in cpu]
+    y, s, sa, g = run_x6(inp, False)
+    ry, rs, rsa = RK.forward(*inp[:6])
+    rg = RK.backward(*inp, rs, rsa)
+    torch.cuda.synchronize()
+    y64, s64, sa64 = O.forward(*cpu[:6])
+    g64 = O.backward(*cpu, s64, sa64)
+    assert O.err_ratio(y.float().cpu().numpy(), y64) <= 1.02 * O.err_ratio(ry.float().cpu().numpy(), y64)
+    assert O.err_ratio(s.cpu().numpy(), s64) <= 2.0 * O.err_ratio(rs.cpu().numpy(), s64) + 1e-7
+    for n, x, r, t in zip(NAMES, g, rg, g64):
+        assert O.err_ratio(x.float().cpu().numpy(), t) <= 1.02 * O.err_ratio(r.float().cpu().numpy(), t), n
+
+
+def test_x6_full_size_slice_vs_reference_kernel_and_properties():
+    """BASELINE cfg2 size (B8 T2048 H12) through the chunked kernels (all 148 SMs, the flag-chained state hand-off under
+    load): one (b,h) slice against the reference kernel run on that slice alone (same strict bounds), and batch/head
+    independence bit for bit."""
+    from oracle import ref_kernel as RK
+    B, T, H = 8, 2048, 12
+    inp = [x.cuda() for x in O.make_inputs(B, T, H, 64, seed=42)]
+    y, s, sa, g = run_x6(inp, True)
+    assert torch.isfinite(y.float()).all() and all(torch.isfinite(x.float()).all() for x in g)
+    sub = [x[3:4, :, 5:6].contiguous() for x in inp]
+    y1, s1, sa1, g1 = run_x6(sub, True)
+    assert torch.equal(y1, y[3:4, :, 5:6]) and torch.equal(sa1, sa[3:4, :, 5:6]) and torch.equal(s1, s[3:4, 5:6])
+    for a_, b_ in zip(g1, g):
+        assert torch.equal(a_, b_[3:4, :, 5:6])
+    if not RK.available():
+        return
+    ry, rs, rsa = RK.forward(*sub[:6])
+    rg = RK.backward(*sub, rs, rsa)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(sa1.cpu().numpy(), rsa.cpu().numpy(), rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(s1.cpu().numpy(), rs[:, :, 3::4].cpu().numpy(), rtol=1e-3, atol=1e-5)
+    yd = O.bf16_ulp_diff(y1.float().cpu().numpy(), ry.float().cpu().numpy())
+    assert (yd == 0).mean() > 0.995 and (yd <= 1).mean() > 0.9995
+    for n, x, r_ in zip(NAMES, g1, rg):
+        xa, ra = x.float().cpu().numpy(), r_.float().cpu().numpy()
+        ok = (O.bf16_ulp_diff(xa, ra) <= 1) | (np.abs(xa - ra) <= 1e-3 * np.sqrt(np.mean(ra ** 2)))
+        assert ok.mean() > 0.999, n
+
+
+def test_x6_forward_state_chaining_is_exact():
     from visualrwkv_b200 import wkv7 as W
     w, q, k, v, a, b = [x.cuda() for x in list(O.make_inputs(2, 256, 2, 64, seed=5))[:6]]
-    W.set_variant(3, 0)
+    W.set_variant(6, 0)
     try:
         y, st = W.wkv7_forward_state(w, q, k, v, a, b)
         h = 128
@@ -218,6 +268,9 @@ def test_chunked_forward_state_chaining_is_exact():
     finally:
         W.set_variant(0, 0)
     assert torch.equal(torch.cat([y1, y2], dim=1), y) and torch.equal(s2, st)
+    cpu = O.make_inputs(2, 256, 2, 64, seed=5)
+    _, _, _, st64 = O.forward(*cpu[:6], want_final_state=True)
+    np.testing.assert_allclose(st.cpu().numpy(), st64, rtol=1e-3, atol=1e-5)
 
 
 def test_bounded_decay_autograd_and_domain_check():
@@ -241,21 +294,58 @@ def test_bounded_decay_autograd_and_domain_check():
 
 
 def test_chunk_granularity_checkpoints_give_the_same_gradients():
-    """VRWKV_WKV7_CHUNK_CHECKPOINTS: one state per 64-step chunk; y is bit-identical, the chunked backward reads the same
-    boundary states from the smaller tensor."""
+    """VRWKV_WKV7_CHUNK_CHECKPOINTS: one state per 64-step chunk.  The two forward variants sum the four 16-step state
+    increments of a chunk in a different order (one accumulator vs four), so the states agree to fp32 round-off, not bit
+    for bit; the chunked backward reads the same boundary states from either tensor."""
     from visualrwkv_b200 import wkv7 as W
     cpu = O.make_inputs(2, 256, 3, 64, seed=31)
     w, q, k, v, a, b, dy = [x.cuda() for x in cpu]
     y0, s0, sa0 = W.forward_raw(w, q, k, v, a, b, bounded_decay=True)
     y1, s1, sa1 = W.forward_raw(w, q, k, v, a, b, bounded_decay=True, chunk_checkpoints=True)
     assert s0.shape[2] == 16 and s1.shape[2] == 4
-    assert torch.equal(y0, y1) and torch.equal(sa0, sa1) and torch.equal(s1, s0[:, :, 3::4])
-    g0 = W.backward_raw(w, q, k, v, a, b, dy, s0, sa0, bounded_decay=True)
-    g1 = W.backward_raw(w, q, k, v, a, b, dy, s1, sa1, bounded_decay=True)
+    np.testing.assert_allclose(s1.cpu().numpy(), s0[:, :, 3::4].cpu().numpy(), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(sa1.cpu().numpy(), sa0.cpu().numpy(), rtol=1e-4, atol=1e-6)
+    yd = O.bf16_ulp_diff(y0.float().cpu().numpy(), y1.float().cpu().numpy())
+    assert (yd == 0).mean() > 0.999 and yd.max() <= 1
+    W.set_variant(0, 7)
+    try:
+        g0 = W.backward_raw(w, q, k, v, a, b, dy, s0, sa0, bounded_decay=True)
+        g1 = W.backward_raw(w, q, k, v, a, b, dy, s1, sa1, bounded_decay=True)
+    finally:
+        W.set_variant(0, 0)
     for x0, x1 in zip(g0, g1):
-        assert torch.equal(x0, x1)
+        assert O.err_ratio(x1.float().cpu().numpy(), x0.float().cpu().numpy().astype(np.float64)) < 2e-4
     with pytest.raises(RuntimeError):  # the flag without the promise is refused
         from visualrwkv_b200 import _lib
         _lib.check(_lib.lib().vrwkv_wkv7_forward_ex(2, 256, 3, _lib.ptr(w), _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(a),
                                                     _lib.ptr(b), _lib.ptr(y1), _lib.ptr(s1), _lib.ptr(sa1), None, None,
                                                     ctypes.c_uint(2), _lib.cur_stream()), "forward_ex")
+
+
+# ------------------------------------------------------------------------------------------------------
+# Round-1 single-pass TF32 chunk kernels (VRWKV_WKV7_TF32): kept for comparison only, never a default.  Their fp32 side
+# outputs carry the TF32 operand rounding (2^-11 per operand): 4-6e-4 RMS on sa / s — OUTSIDE the north-star tolerance,
+# which is why the bounds below are RMS bounds and why nothing benchmarks or ships this path.
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bwd_variant", [5, 3], ids=["chunked-bwd", "segmented-bwd"])
+@pytest.mark.parametrize("shape,kind,seed", [((2, 512, 3), "realistic", 5), ((2, 256, 2), "stress", 8)])
+def test_tf32_comparison_path_rms_bounds(shape, kind, seed, bwd_variant):
+    from visualrwkv_b200 import wkv7 as W
+    B, T, H = shape
+    cpu = O.make_inputs(B, T, H, 64, seed=seed, kind=kind)
+    w, q, k, v, a, b, dy = [x.cuda() for x in cpu]
+    y, s, sa = W.forward_raw(w, q, k, v, a, b, bounded_decay=True, tf32=True)
+    W.set_variant(0, bwd_variant)
+    try:
+        g = W.backward_raw(w, q, k, v, a, b, dy, s, sa, bounded_decay=True, tf32=True)
+    finally:
+        W.set_variant(0, 0)
+    W.domain_check()
+    y64, s64, sa64 = O.forward(*cpu[:6])
+    assert O.err_ratio(y.float().cpu().numpy(), y64) < 2.2e-3
+    assert O.err_ratio(sa.cpu().numpy(), sa64) < 1.2e-3
+    assert O.err_ratio(s.cpu().numpy(), s64) < 1.2e-3
+    g64 = O.backward(*cpu, s64, sa64)
+    tol = 2.4e-3 if kind == "realistic" else 4.5e-3
+    for n, x, r in zip(NAMES, g, g64):
+        assert O.err_ratio(x.float().cpu().numpy(), r) < tol, n

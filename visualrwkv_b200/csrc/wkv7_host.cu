@@ -181,7 +181,8 @@ static int launch_x6_fwd(const void* const* in, const Wkv7FwdArgs& a, bool chunk
     VRWKV_CUDA(cudaMemsetAsync(ws, 0, sync_bytes, st));
     X6FwdArgs xa{a.B, a.T, a.H, a.y, a.s, a.sa, a.state_in, a.state_out, chain_bytes ? (float*)(ws + sync_bytes) : nullptr, (int*)ws};
     const size_t smem = sizeof(X6FwdSmem) + 1024;
-    auto kern = chunk_ck ? wkv7_x6_fwd_kernel<false> : wkv7_x6_fwd_kernel<true>;
+    // 16-step checkpoints only when a checkpoint tensor in the reference's layout was asked for
+    auto kern = (chunk_ck || !a.s) ? wkv7_x6_fwd_kernel<false> : wkv7_x6_fwd_kernel<true>;
     VRWKV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = nitems < sm_count() ? nitems : sm_count();
     kern<<<grid, X6_THREADS, smem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], xa);
