@@ -420,6 +420,21 @@ wkv7_x3_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
                 mma_x3<64, 1, 1>(tmem + C_DS0, b4, O_DRDY, 16384, O_AQ, 16384, false);                        // dR^T At
                 mma_x2a<64, 1, 1>(tmem + C_DS0, b4, O_DRDY + BT_BYTES, O_AQ + BT_BYTES, 16384, true);         // dY^T Qt
                 umma_commit(&sm.bar_c3);
+            }
+            __syncwarp();
+        }
+        // ================= P5: publish dS_0 = dZ + dR^T At + dY^T Qt (the previous chunk is waiting for it) =================
+        mbar_wait(&sm.bar_c3, ph_c3 & 1);
+        ph_c3++;
+        tc_fence_after();
+        __syncwarp();
+        uint32_t ds0v[16];
+        if (c > 0 && r < N) tmem_ld16(tm_row + C_DS0 + 16 * cs, ds0v);
+        tc_fence_before();
+        __syncthreads();
+        if (warp == 0) {
+            if (elect_one()) {
+                tc_fence_after();
                 mma_x3<128, 0, 0>(tmem + C_DA, b4, O_DRDY, 16384, O_R2, 16384, false);                        // dA = [dR;dY][U;V]^T
                 mma_x3<128, 0, 0>(tmem + C_DAT, b4, O_R2, 16384, O_DRDY, 16384, false);                       // dA^T
                 mma_x3<64, 0, 0>(tmem + C_AQ, b4, O_DRDY, 16384, O_S0P, BT_BYTES, false);                     // [dR;dY] S_0
@@ -429,15 +444,9 @@ wkv7_x3_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
             }
             __syncwarp();
         }
-        // ================= P5: publish dS_0 = dZ + dR^T At + dY^T Qt =================
-        mbar_wait(&sm.bar_c3, ph_c3 & 1);
-        ph_c3++;
-        tc_fence_after();
-        __syncwarp();
         if (c > 0) {
             if (r < N) {
-                uint32_t v[16];
-                tmem_ld16(tm_row + C_DS0 + 16 * cs, v);
+                const uint32_t* v = ds0v;
                 float4* dst = reinterpret_cast<float4*>(ds_out + (size_t)r * N + 16 * cs);
 #pragma unroll
                 for (int c4 = 0; c4 < 4; c4++) {
@@ -450,10 +459,9 @@ wkv7_x3_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
                     dst[c4] = make_float4(z.x + __uint_as_float(v[4 * c4]), z.y + __uint_as_float(v[4 * c4 + 1]), z.z + __uint_as_float(v[4 * c4 + 2]),
                                           z.w + __uint_as_float(v[4 * c4 + 3]));
                 }
-                __threadfence();
             }
-            tc_fence_before();
             __syncthreads();
+            // release at gpu scope is cumulative: the stores of all threads are ordered before it by the CTA barrier
             if (tid == 0) st_release(p.sync + 1 + bh, nch - c);
         }
         stamp();  // 9
@@ -515,6 +523,9 @@ wkv7_x3_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
             ein[1][0] = __ldg(reinterpret_cast<const uint4*>(src1 + ego));
             ein[1][1] = __ldg(reinterpret_cast<const uint4*>(src1 + ego) + 1);
         }
+        float wpre[8];   // w of this thread's 8 rows in the dw pass (column tid & 63)
+#pragma unroll
+        for (int k = 0; k < 8; k++) wpre[k] = bf16lo_to_f32((uint32_t)__ldg(p.w + row0 + (size_t)(8 * (tid >> 6) + k) * rstride + (tid & 63)));
         mma_wait();
         stamp();  // 12
         item = sm.next_item;
@@ -613,7 +624,7 @@ wkv7_x3_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
             for (int k = 0; k < 8; k++) {
                 const int t = 8 * rg + k;
                 const size_t go = row0 + (size_t)t * rstride + j;
-                const float g = -__expf(bf16lo_to_f32((uint32_t)__ldg(p.w + go)));
+                const float g = -__expf(wpre[k]);
                 p.dw[go] = f32_to_bf16_bits((dG[k] + off) * g);
             }
         }

@@ -167,10 +167,11 @@ wkv7_x6_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
             *reinterpret_cast<float2*>(&sm.esc[rg * N + j0]) = make_float2(c0[3], c1[3]);
             __syncthreads();
             float pre0 = 1.f, pre1 = 1.f;
-            for (int g = 0; g < rg; g++) {
+#pragma unroll
+            for (int g = 0; g < 15; g++) {   // all loads in flight at once; groups >= rg contribute a factor 1
                 const float2 pp = *reinterpret_cast<const float2*>(&sm.esc[g * N + j0]);
-                pre0 *= pp.x;
-                pre1 *= pp.y;
+                pre0 *= (g < rg) ? pp.x : 1.f;
+                pre1 *= (g < rg) ? pp.y : 1.f;
             }
             float Ep0 = pre0, Ep1 = pre1;
 #pragma unroll
@@ -506,10 +507,10 @@ wkv7_x6_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
 #pragma unroll
                 for (int c4 = 0; c4 < 4; c4++) dst[c4] = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
             }
-            __threadfence();
         }
         tc_fence_before();
         __syncthreads();
+        // release at gpu scope is cumulative: the state stores of all threads are ordered before it by the CTA barrier
         if (tid == 0) st_release(p.sync + 1 + bh, c + 1);
         stamp();  // 16: item done
         lt++;
