@@ -229,9 +229,13 @@ class TmixBlockFn(torch.autograd.Function):
         x2 = x.reshape(rows, C).contiguous()
         coefs = [c.reshape(C) for c in (x_r, x_w, x_k, x_v, x_a, x_g)]
         (xr, xw, xk, xv, xa, xg), _, stats = ln_mix_forward(x2, T, ln_w if with_ln else None, ln_b if with_ln else None, ln_eps, coefs)
-        r = xr @ Wr.t()
-        k = xk @ Wk.t()
-        v = xv @ Wv.t()
+        own = gemm2_supported(rows, C, C)   # CTA-pair tcgen05 GEMMs (csrc/gemm2_sm100.cu); cuBLAS only for shapes it cannot tile
+        if own:
+            r, k, v = gemm2_grouped([xr, xk, xv], [Wr, Wk, Wv])   # one launch: 3 x (rows x C x C)
+        else:
+            r = xr @ Wr.t()
+            k = xk @ Wk.t()
+            v = xv @ Wv.t()
         hw = torch.tanh(xw @ w1)
         ww = hw @ w2
         ha = xa @ a1
@@ -251,8 +255,8 @@ class TmixBlockFn(torch.autograd.Function):
         v4 = lambda t: t.view(B, T, H, 64)
         y, s, sa = wkv7_fwd_raw(v4(w), v4(r), v4(k2), v4(v2_), v4(nkk), v4(kka))
         z = tmix_post_forward(y.view(rows, C), r, k2, v2_, g, lnx_w, lnx_b, r_k.reshape(C), gn_eps)
-        if gemm_supported(rows, C, C):
-            out = gemm_tn(z, Wo, EPI_ADD, x2) if with_ln else gemm_tn(z, Wo, EPI_NONE)
+        if own:
+            out = gemm2(z, Wo, G2_TN, EPI_ADD, x2) if with_ln else gemm2(z, Wo)
         else:
             out = torch.addmm(x2, z, Wo.t()) if with_ln else z @ Wo.t()
         ctx.save_for_backward(x2, stats, ln_w, ln_b, *coefs, xr, xw, xk, xv, xa, xg, r, k, v, hw, ww, ha, aa, hg, g, hv, vv, vf2,
@@ -273,8 +277,8 @@ class TmixBlockFn(torch.autograd.Function):
         rows = B * T
         has_vres = layer_id != 0
         do = dout.reshape(rows, C).contiguous()
-        dz = do @ Wo
-        dWo = do.t() @ z
+        own = gemm2_supported(rows, C, C) and gemm2_supported(C, C, rows)
+        dz = gemm2(do, Wo, G2_NN) if own else do @ Wo
         dy, dr, dk2a, dv2a, dg, red3 = tmix_post_backward(y.view(rows, C), r, k2, v2_, g, lnx_w, lnx_b, r_k.reshape(C), gn_eps, dz)
         v4 = lambda t: t.view(B, T, H, 64)
         dw, dq, dk2b, dv2b, dnkk, dkka = wkv7_bwd_raw(v4(w), v4(r), v4(k2), v4(v2_), v4(nkk), v4(kka), v4(dy), s, sa)
@@ -300,19 +304,29 @@ class TmixBlockFn(torch.autograd.Function):
         dxa = dha @ a1.t()
         da1 = xa.t() @ dha
         # main projections
-        dxr = dr @ Wr
-        dWr = dr.t() @ xr
-        dxk = dk @ Wk
-        dWk = dk.t() @ xk
-        dWv = dv.t() @ xv
         if has_vres:
             dhv = dvv @ v2.t()
             dv2p = hv.t() @ dvv
             dv1 = xv.t() @ dhv
-            dxv = torch.addmm(dhv @ v1.t(), dv, Wv)
         else:
-            dxv = dv @ Wv
             dv2p = dv1 = None
+        if own:
+            # dgrad: dx = dy W (W is [out, in]: contraction over its rows); wgrad: dW = dy^T x over the token rows, the
+            # four C x C weight gradients of the block in one split-K launch
+            if has_vres:
+                dxr, dxk = gemm2_grouped([dr, dk], [Wr, Wk], G2_NN)
+                dxv = gemm2(dv, Wv, G2_NN, EPI_ADD, dhv @ v1.t())
+            else:
+                dxr, dxk, dxv = gemm2_grouped([dr, dk, dv], [Wr, Wk, Wv], G2_NN)
+            dWo, dWr, dWk, dWv = gemm2_grouped([do, dr, dk, dv], [z, xr, xk, xv], G2_TT, ksplit=_ksplit(4, C, C, rows))
+        else:
+            dWo = do.t() @ z
+            dxr = dr @ Wr
+            dWr = dr.t() @ xr
+            dxk = dk @ Wk
+            dWk = dk.t() @ xk
+            dWv = dv.t() @ xv
+            dxv = torch.addmm(dhv @ v1.t(), dv, Wv) if has_vres else dv @ Wv
         coefs = [c_r, c_w, c_k, c_v, c_a, c_g]
         dx, dlnw, dlnb, dco = ln_mix_backward(x2, T, stats, ln_w if with_ln else None, ln_b if with_ln else None, coefs,
                                               [dxr, dxw, dxk, dxv, dxa, dxg], dresid=do if with_ln else None)
@@ -338,11 +352,11 @@ class CmixBlockFn(torch.autograd.Function):
         ck = x_k.reshape(C)
         (xk,), _, stats = ln_mix_forward(x2, T, ln_w if with_ln else None, ln_b if with_ln else None, ln_eps, [ck])
         M, Hd = rows, Wkey.shape[0]
-        if gemm_supported(M, Hd, C) and gemm_supported(M, C, Hd):
+        if gemm2_supported(M, Hd, C) and gemm2_supported(M, C, Hd):
             # key GEMM with relu^2 in the tcgen05 epilogue (the 4C-wide pre-activation never touches HBM), value GEMM
             # with the residual add in the epilogue
-            act = gemm_tn(xk, Wkey, EPI_RELU_SQ)
-            out = gemm_tn(act, Wval, EPI_ADD, x2) if with_ln else gemm_tn(act, Wval, EPI_NONE)
+            act = gemm2(xk, Wkey, G2_TN, EPI_RELU_SQ)
+            out = gemm2(act, Wval, G2_TN, EPI_ADD, x2) if with_ln else gemm2(act, Wval)
             hk = None
         else:
             hk = xk @ Wkey.t()
@@ -357,11 +371,18 @@ class CmixBlockFn(torch.autograd.Function):
         x2, stats, ln_w, ln_b, ck, xk, hk, act, Wkey, Wval = ctx.saved_tensors
         B, T, C, with_ln = ctx.meta
         do = dout.reshape(B * T, C).contiguous()
-        dact = do @ Wval
-        dWval = do.t() @ act
-        dhk = relu_sq_backward(hk, dact) if hk is not None else relu_sq_backward_from_act(act, dact)
-        dxk = dhk @ Wkey
-        dWkey = dhk.t() @ xk
+        rows, Hd = B * T, Wkey.shape[0]
+        if hk is None and gemm2_supported(rows, Hd, C) and gemm2_supported(rows, C, Hd) and gemm2_supported(C, Hd, rows) and gemm2_supported(Hd, C, rows):
+            dhk = gemm2(do, Wval, G2_NN, EPI_RELUSQ_BWD, act)     # dact = do Wval and d relu()^2 in one pass: dact never reaches HBM
+            dxk = gemm2(dhk, Wkey, G2_NN)
+            # both weight gradients in one launch of C x 4C problems: dWval = do^T act, dWkey = (xk^T dhk)^T (stored transposed)
+            dWval, dWkey = gemm2_grouped([do, xk], [act, dhk], G2_TT, ksplit=1, transposed=[0, 1])
+        else:
+            dact = do @ Wval
+            dWval = do.t() @ act
+            dhk = relu_sq_backward(hk, dact) if hk is not None else relu_sq_backward_from_act(act, dact)
+            dxk = dhk @ Wkey
+            dWkey = dhk.t() @ xk
         dx, dlnw, dlnb, dco = ln_mix_backward(x2, T, stats, ln_w if with_ln else None, ln_b if with_ln else None, [ck], [dxk],
                                               dresid=do if with_ln else None)
         return (dx.view(B, T, C), dlnw if with_ln else None, dlnb if with_ln else None, dco[0].view(1, 1, C),
@@ -385,7 +406,8 @@ class HeadLossFn(torch.autograd.Function):
         V = weight.shape[0]
         rows = B * T
         x2 = x.reshape(rows, C).contiguous()
-        logits = x2 @ weight.t()
+        own = HEAD_OWN_GEMM and gemm2_supported(rows, V, C) and gemm2_supported(V, C, rows) and gemm2_supported(rows, C, V)
+        logits = gemm2(x2, weight) if own else x2 @ weight.t()
         labels = labels.contiguous()
         assert labels.dtype == torch.int64 and labels.shape == (B, T)
         lse = torch.empty(rows, dtype=torch.float32, device=x.device)
@@ -414,8 +436,12 @@ class HeadLossFn(torch.autograd.Function):
         _chk(L.vrwkv_ce_backward(_c_int(rows), _c_int(T), _c_int(V), _c_int(ignore_index), _p(logits), _p(labels), _p(lse), _p(rmax),
                                  _p(amax), _p(wrow), _c_float(l2), _lib.cur_stream()), "vrwkv_ce_backward")
         dlogits = logits  # overwritten in place
-        dx = dlogits @ weight
-        dW = dlogits.t() @ x2
+        if HEAD_OWN_GEMM and gemm2_supported(rows, V, C) and gemm2_supported(V, C, rows) and gemm2_supported(rows, C, V):
+            dx = gemm2(dlogits, weight, G2_NN)
+            dW = gemm2(dlogits, x2, G2_TT, ksplit=_ksplit(1, V, C, rows))
+        else:
+            dx = dlogits @ weight
+            dW = dlogits.t() @ x2
         return dx.view(B, T, C), dW, None, None
 
 
@@ -440,3 +466,50 @@ def gemm_tn(a, w, epilogue=EPI_NONE, residual=None):
 
 def gemm_supported(M, N, K):
     return K % 64 == 0 and N % 128 == 0 and M > 0
+
+
+# ------------------------------------------------------------------------------------------------------
+# CTA-pair tcgen05 GEMM, all layouts (csrc/gemm2_sm100.cu)
+# ------------------------------------------------------------------------------------------------------
+G2_TN, G2_NN, G2_TT = 0, 2, 3     # layout bits: 1 = A stored [K,M], 2 = B stored [K,N]
+
+
+def gemm2_grouped(As, Bs, layout=G2_TN, epilogue=EPI_NONE, residuals=None, ksplit=1, transposed=None):
+    """[epilogue(op(a) . op(b)) for a, b in zip(As, Bs)] in ONE launch (identical shapes), bf16 in / out, fp32 accumulate.
+      G2_TN: a [M,K], b [N,K]  -> a @ b.T      (forward y = x W^T)
+      G2_NN: a [M,K], b [K,N]  -> a @ b        (dgrad  dx = dy W)
+      G2_TT: a [K,M], b [K,N]  -> a.T @ b      (wgrad  dW = dy^T x; ksplit > 1 slices the long contraction)"""
+    L = _lib.lib()
+    a, b = As[0], Bs[0]
+    _bf16c(*As, *Bs, *(residuals or []))
+    a_mn, b_mn = layout & 1, (layout >> 1) & 1
+    M, K = (a.shape[1], a.shape[0]) if a_mn else a.shape
+    N = b.shape[1] if b_mn else b.shape[0]
+    assert (b.shape[0] if b_mn else b.shape[1]) == K and all(x.shape == a.shape for x in As) and all(x.shape == b.shape for x in Bs)
+    tr = list(transposed) if transposed else [0] * len(As)
+    Cs = [torch.empty((N, M) if t else (M, N), dtype=torch.bfloat16, device=a.device) for t in tr]   # transposed[g]: C[g] = (a.b)^T
+    _chk(L.vrwkv_gemm2_bf16_grouped(_c_int(M), _c_int(N), _c_int(K), _c_int(len(As)), _parr(As), _parr(Bs), _parr(Cs),
+                                    _parr(residuals) if residuals else None, (_c_int * len(tr))(*tr), _c_int(layout), _c_int(epilogue),
+                                    _c_int(ksplit), _lib.cur_stream()), "vrwkv_gemm2_bf16_grouped")
+    return Cs
+
+
+def gemm2(a, b, layout=G2_TN, epilogue=EPI_NONE, residual=None, ksplit=1):
+    return gemm2_grouped([a], [b], layout, epilogue, [residual] if residual is not None else None, ksplit)[0]
+
+
+EPI_RELUSQ_BWD = 4
+HEAD_OWN_GEMM = os.environ.get("VRWKV_HEAD_GEMM", "own") == "own"   # "cublas": library GEMMs for the three head products
+
+
+def gemm2_supported(M, N, K, ksplit=1):
+    return K % (64 * ksplit) == 0 and N % 128 == 0 and M % 8 == 0 and M > 0
+
+
+def _ksplit(groups, M, N, K):
+    """Slices of the contraction for a weight gradient: enough (group, tile, slice) items for the 74 CTA pairs."""
+    tiles = groups * ((M + 255) // 256) * (N // (256 if N % 256 == 0 else 128))
+    ks = 1
+    while ks < 8 and tiles * ks < 74 and K % (64 * ks * 2) == 0:
+        ks *= 2
+    return ks
