@@ -170,6 +170,40 @@ int vrwkv_ce_backward(int rows, int T, int V, int ignore_index, uint16_t* logits
 int vrwkv_gemm_bf16_tn(int M, int N, int K, const uint16_t* A, const uint16_t* B, uint16_t* C, int epilogue,
                        const uint16_t* R, void* stream);
 
+/* CTA-pair GEMM (tcgen05.mma.cta_group::2, 256-row tiles across two SMs), every layout of the forward and backward
+ * products of model.py:175-194,225-227,325:   C[g] = epilogue(op(A[g]) . op(B[g])), g < ngroups problems of one shape in
+ * one launch.  layout bit 0: A is [K,M] (else [M,K]); bit 1: B is [K,N] (else [N,K], the nn.Linear weight layout).
+ * epilogue 0 none, 1 relu(.)^2, 2 + R[g], 4 (.) * 2 sqrt(R[g]) (backward of relu^2 from the saved activation),
+ * 5 + bias[g][n], 6 tanh-GELU(. + bias), 7 . + bias + R[g][row % r_rows] (the SigLIP tower's Linear layers).
+ * ksplit > 1 slices the contraction (weight gradients over the 16384 token rows): slices meet in an internal fp32
+ * workspace and the last one writes the bf16 result; c_transposed[g] != 0 stores C[g] as [N,M].
+ * K % (64 ksplit) == 0, N % 128 == 0, M % 8 == 0 for layout bit 0. */
+int vrwkv_gemm2_bf16_grouped(int M, int N, int K, int ngroups, const uint16_t* const* A, const uint16_t* const* B,
+                             uint16_t* const* C, const uint16_t* const* R, const int* c_transposed, int layout,
+                             int epilogue, int ksplit, const uint16_t* const* bias, int r_rows, void* stream);
+int vrwkv_gemm2_bf16(int M, int N, int K, const uint16_t* A, const uint16_t* B, uint16_t* C, int layout, int epilogue,
+                     const uint16_t* R, int ksplit, void* stream);
+
+/* VisualRWKV.preparing_embedding (model.py:473-494): out[t] = emb[ids[t]], except that the k-th token (row-major over the
+ * batch) with ids == image_token_index takes feats[k] (bit-exact row copies).  *n_slots_out (device int, may be NULL)
+ * receives the number of image-token slots; slots beyond nfeat keep the embedding row.  The backward gathers dout rows
+ * back into feature order (rows without a slot are zero).  D % 8 == 0. */
+int vrwkv_embed_scatter_forward(int ntok, int D, int nfeat, long long image_token_index, const long long* ids,
+                                const uint16_t* emb, const uint16_t* feats, uint16_t* out, int* n_slots_out, void* stream);
+int vrwkv_embed_scatter_backward(int ntok, int D, int nfeat, long long image_token_index, const long long* ids,
+                                 const uint16_t* dout, uint16_t* dfeats, void* stream);
+/* VisualRWKV.adaptive_pooling (model.py:442-447): x [N, hw*hw, D] -> AdaptiveAvgPool2d(out) -> y [N, out*out, D]. */
+int vrwkv_adaptive_pool(int N, int hw, int out, int D, const uint16_t* x, uint16_t* y, void* stream);
+
+/* SigLIP self-attention, forward only (transformers SiglipAttention as called by VisualRWKV-v7/v7.01/src/model.py:347-352,
+ * 448-454): q, k, v, o are [N*S, 64*H] bf16 (heads side by side); softmax(q k^T / 8) v per (image, head).  S <= 256. */
+int vrwkv_vit_attention(int N, int S, int H, const uint16_t* q, const uint16_t* k, const uint16_t* v, uint16_t* o, void* stream);
+/* pixels [N,3,Hp*P,Wp*P] -> patch rows [N*Hp*Wp, 3*P*P] in Conv2d weight order (the patch embedding becomes a GEMM). */
+int vrwkv_im2col_patches(int N, int Hp, int Wp, int P, const uint16_t* pixels, uint16_t* out, void* stream);
+/* MLPWithContextGating's gate (model.py:335-338): h = x * sigmoid(g), and its backward (dx may be NULL). n % 8 == 0. */
+int vrwkv_sigmul_forward(size_t n, const uint16_t* x, const uint16_t* g, uint16_t* h, void* stream);
+int vrwkv_sigmul_backward(size_t n, const uint16_t* x, const uint16_t* g, const uint16_t* dh, uint16_t* dx, uint16_t* dg, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

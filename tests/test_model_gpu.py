@@ -112,22 +112,72 @@ def test_scatter_is_bit_exact_and_ordered():
     assert torch.equal(f.grad, torch.full_like(f, 1.0))
 
 
-def test_vit_matches_hf_siglip_on_gpu():
+@pytest.mark.parametrize("name,hf_kw,N", [
+    ("siglip-tiny-test", dict(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256, image_size=64, patch_size=16), 3),
+    # the real tower of BASELINE cfg2: SigLIP-B/16 @ 224 -> 196 patches (random weights: no checkpoints offline)
+    ("siglip-base-patch16-224", dict(hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072, image_size=224, patch_size=16), 2),
+    ("siglip-base-patch16-256", dict(hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072, image_size=256, patch_size=16), 1),
+])
+def test_vit_matches_hf_siglip_on_gpu(name, hf_kw, N):
+    """Our tower (im2col + CTA-pair GEMMs with bias/GELU/residual epilogues + the tcgen05 attention kernel + LayerNorm
+    kernels) against transformers' SiglipVisionModel in fp32 on the CPU, same weights."""
     transformers = pytest.importorskip("transformers")
+    from visualrwkv_b200 import fused
     from visualrwkv_b200.vision import SiglipVisionTower
-    cfg = transformers.SiglipVisionConfig(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256,
-                                          image_size=64, patch_size=16)
+    cfg = transformers.SiglipVisionConfig(**hf_kw)
     torch.manual_seed(0)
     hf = transformers.SiglipVisionModel(cfg).eval()
-    tower = SiglipVisionTower("siglip-tiny-test")
+    tower = SiglipVisionTower(name)
     missing, unexpected = tower.load_state_dict(hf.state_dict(), strict=False)
     assert not missing, missing  # every tower parameter exists in the HF checkpoint layout
-    px = torch.randn(3, 3, 64, 64)
+    px = torch.randn(N, 3, hf_kw["image_size"], hf_kw["image_size"])
     with torch.no_grad():
-        ref = hf(pixel_values=px).last_hidden_state
+        ref = hf(pixel_values=px.to(torch.bfloat16).float()).last_hidden_state
+    from visualrwkv_b200 import wkv7
+    n0 = wkv7.launch_count()
     out = tower.to("cuda", torch.bfloat16)(px.to("cuda", torch.bfloat16))
+    assert wkv7.launch_count() - n0 >= 2 + 7 * hf_kw["num_hidden_layers"]   # the tower ran on this library's kernels, not on a fallback
     assert out.shape == ref.shape
     assert _rel(out, ref) < 3e-2
+
+
+def test_vit_attention_kernel_vs_sdpa():
+    from visualrwkv_b200 import _lib, fused
+    torch.manual_seed(1)
+    for (N, S, H) in [(2, 196, 12), (1, 256, 4), (3, 16, 2), (1, 100, 1)]:
+        q, k, v = [(torch.randn(N * S, 64 * H, device="cuda")).to(torch.bfloat16) for _ in range(3)]
+        o = torch.empty_like(q)
+        fused._chk(_lib.lib().vrwkv_vit_attention(N, S, H, fused._p(q), fused._p(k), fused._p(v), fused._p(o), _lib.cur_stream()), "attn")
+        f = lambda t: t.view(N, S, H, 64).transpose(1, 2).float()
+        ref = torch.nn.functional.scaled_dot_product_attention(f(q), f(k), f(v)).transpose(1, 2).reshape(N * S, 64 * H)
+        assert _rel(o, ref) < 6e-3, (N, S, H)
+
+
+def test_adaptive_pool_and_projector_kernels():
+    from visualrwkv_b200 import ops
+    from visualrwkv_b200.model import MLPWithContextGating
+    torch.manual_seed(2)
+    x = torch.randn(3, 196, 768, device="cuda").to(torch.bfloat16)
+    for out_hw in (24, 7, 14):
+        y = ops.adaptive_pooling(x, out_hw)
+        ref = torch.nn.functional.adaptive_avg_pool2d(x.float().view(3, 14, 14, 768).permute(0, 3, 1, 2), out_hw).reshape(3, 768, -1).permute(0, 2, 1)
+        assert y.shape == ref.shape and _rel(y, ref) < 3e-3
+    m = MLPWithContextGating(768, 768).to("cuda", torch.bfloat16)
+    xin = torch.randn(2, 576, 768, device="cuda").to(torch.bfloat16)
+    g = torch.randn(2, 576, 768, device="cuda").to(torch.bfloat16)
+    xa = xin.clone().requires_grad_(True)
+    ya = ops.projector_forward(m, xa)
+    ya.backward(g)
+    mine = {n: p.grad.clone() for n, p in m.named_parameters()}
+    m.zero_grad()
+    xb = xin.clone().float().requires_grad_(True)
+    P = {n: p.detach().float().requires_grad_(True) for n, p in m.named_parameters()}
+    hb = xb * torch.sigmoid(xb @ P["gate.weight"].t())
+    yb = torch.nn.functional.layer_norm(hb @ P["o_proj.weight"].t(), (768,), P["ln_v.weight"], P["ln_v.bias"], m.ln_v.eps)
+    yb.backward(g.float())
+    assert _rel(ya, yb) < 1e-2 and _rel(xa.grad, xb.grad) < 3e-2
+    for n in mine:
+        assert _rel(mine[n], P[n].grad) < 3e-2, n
 
 
 def test_bench_line_keys():

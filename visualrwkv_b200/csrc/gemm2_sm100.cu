@@ -37,7 +37,8 @@ namespace vrwkv {
 
 constexpr int G2_BM = 128;     // rows per CTA (256 per pair)
 constexpr int G2_BK = 64;
-enum { G2_EPI_NONE = 0, G2_EPI_RELU_SQ = 1, G2_EPI_ADD = 2, G2_EPI_ATOMIC_F32 = 3, G2_EPI_RELUSQ_BWD = 4 };
+enum { G2_EPI_NONE = 0, G2_EPI_RELU_SQ = 1, G2_EPI_ADD = 2, G2_EPI_ATOMIC_F32 = 3, G2_EPI_RELUSQ_BWD = 4,
+       G2_EPI_BIAS = 5, G2_EPI_BIAS_GELU = 6, G2_EPI_BIAS_ADD = 7 };   // the SigLIP tower's Linear layers (bias; tanh-GELU; + residual)
 
 constexpr int G2_MAXG = 4;   // problems of identical shape in one launch (r/k/v projections, the four C x C weight gradients, ...)
 struct Gemm2Args {
@@ -47,6 +48,8 @@ struct Gemm2Args {
     uint16_t* C[G2_MAXG];
     const uint16_t* R[G2_MAXG];  // residual (EPI_ADD)
     int ct[G2_MAXG];             // 1: store this group's result transposed (C[g] is [N,M]); EPI_NONE only
+    const uint16_t* bias[G2_MAXG];  // [N] (EPI_BIAS*)
+    int r_rows;                  // rows of R (EPI_BIAS_ADD: R row = row % r_rows — a position table shared by all images); 0 = M
     float* Cf;          // ATOMIC_F32: fp32 partial sums [ngroups][M][N]; must be zero on entry, is zero again on exit
     int* tickets;       // ATOMIC_F32: one counter per (group, tile, CTA of the pair); zero on entry and on exit
 };
@@ -231,10 +234,21 @@ gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
                     } else {
                         uint4 out[4], res[4];
                         uint32_t* o = reinterpret_cast<uint32_t*>(out);
+                        uint4 bia[4];
                         if (EPI == G2_EPI_ADD || EPI == G2_EPI_RELUSQ_BWD) {
 #pragma unroll
                             for (int i = 0; i < 4; i++) res[i] = *reinterpret_cast<const uint4*>(Rg + off + 8 * i);
                         }
+                        if (EPI == G2_EPI_BIAS || EPI == G2_EPI_BIAS_GELU || EPI == G2_EPI_BIAS_ADD) {
+#pragma unroll
+                            for (int i = 0; i < 4; i++) bia[i] = __ldg(reinterpret_cast<const uint4*>(p.bias[g] + n0 + c + 8 * i));
+                            if (EPI == G2_EPI_BIAS_ADD) {
+                                const size_t roff = (size_t)(p.r_rows ? row % p.r_rows : row) * p.N + n0 + c;
+#pragma unroll
+                                for (int i = 0; i < 4; i++) res[i] = *reinterpret_cast<const uint4*>(Rg + roff + 8 * i);
+                            }
+                        }
+                        const uint32_t* bb = reinterpret_cast<const uint32_t*>(bia);
                         const uint32_t* rr = reinterpret_cast<const uint32_t*>(res);
 #pragma unroll
                         for (int i = 0; i < 16; i++) {
@@ -248,6 +262,17 @@ gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
                             } else if (EPI == G2_EPI_ADD) {
                                 x0 += bf16lo_to_f32(rr[i]);
                                 x1 += bf16hi_to_f32(rr[i]);
+                            } else if (EPI == G2_EPI_BIAS || EPI == G2_EPI_BIAS_GELU || EPI == G2_EPI_BIAS_ADD) {
+                                // nn.Linear in bf16: one rounding after the bias; then the tanh-GELU / residual add of the eager graph
+                                x0 = __bfloat162float(__float2bfloat16_rn(x0 + bf16lo_to_f32(bb[i])));
+                                x1 = __bfloat162float(__float2bfloat16_rn(x1 + bf16hi_to_f32(bb[i])));
+                                if (EPI == G2_EPI_BIAS_GELU) {
+                                    x0 = 0.5f * x0 * (1.f + tanhf(0.7978845608028654f * (x0 + 0.044715f * x0 * x0 * x0)));
+                                    x1 = 0.5f * x1 * (1.f + tanhf(0.7978845608028654f * (x1 + 0.044715f * x1 * x1 * x1)));
+                                } else if (EPI == G2_EPI_BIAS_ADD) {
+                                    x0 += bf16lo_to_f32(rr[i]);
+                                    x1 += bf16hi_to_f32(rr[i]);
+                                }
                             } else if (EPI == G2_EPI_RELUSQ_BWD) {
                                 // eager graph: dact -> bf16, then d/dx relu(x)^2 = 2 relu(x) = 2 sqrt(act)
                                 x0 = __bfloat162float(__float2bfloat16_rn(x0)) * 2.f * sqrtf(bf16lo_to_f32(rr[i]));
@@ -362,7 +387,7 @@ static int g2_workspace(size_t cf_elems, size_t n_tickets, cudaStream_t st, G2Wo
 // writes the bf16 result (no element-wise epilogue in that mode).
 extern "C" int vrwkv_gemm2_bf16_grouped(int M, int N, int K, int ngroups, const uint16_t* const* A, const uint16_t* const* B,
                                         uint16_t* const* C, const uint16_t* const* R, const int* c_transposed, int layout, int epilogue,
-                                        int ksplit, void* stream) {
+                                        int ksplit, const uint16_t* const* bias, int r_rows, void* stream) {
     if (M <= 0 || N <= 0 || K <= 0) return vrwkv_fail(VRWKV_EINVAL, "gemm2: bad shape (%d,%d,%d)", M, N, K);
     if (ngroups < 1 || ngroups > G2_MAXG) return vrwkv_fail(VRWKV_EINVAL, "gemm2: 1..%d groups (got %d)", G2_MAXG, ngroups);
     if (ksplit < 1) ksplit = 1;
@@ -371,15 +396,17 @@ extern "C" int vrwkv_gemm2_bf16_grouped(int M, int N, int K, int ngroups, const 
     const int a_mn = layout & 1, b_mn = (layout >> 1) & 1;
     if (a_mn && (M % 8)) return vrwkv_fail(VRWKV_EUNSUP, "gemm2: M=%d must be a multiple of 8 when A is stored [K,M]", M);
     if (ksplit > 1 && epilogue != G2_EPI_NONE) return vrwkv_fail(VRWKV_EINVAL, "gemm2: no element-wise epilogue with ksplit > 1");
-    if (epilogue != G2_EPI_NONE && epilogue != G2_EPI_RELU_SQ && epilogue != G2_EPI_ADD && epilogue != G2_EPI_RELUSQ_BWD)
-        return vrwkv_fail(VRWKV_EINVAL, "gemm2: unknown epilogue %d", epilogue);
+    if (epilogue < 0 || epilogue > G2_EPI_BIAS_ADD || epilogue == G2_EPI_ATOMIC_F32) return vrwkv_fail(VRWKV_EINVAL, "gemm2: unknown epilogue %d", epilogue);
+    const bool need_r = epilogue == G2_EPI_ADD || epilogue == G2_EPI_RELUSQ_BWD || epilogue == G2_EPI_BIAS_ADD;
+    const bool need_b = epilogue >= G2_EPI_BIAS;
+    if (need_b && (layout != 0 || !bias)) return vrwkv_fail(VRWKV_EINVAL, "gemm2: bias epilogues need the [M,K] x [N,K] layout and a bias per group");
     const int BN = (N % 256 == 0) ? 256 : 128;
     cudaStream_t st = (cudaStream_t)stream;
     Gemm2Maps maps;
     Gemm2Args a{};
-    a.M = M; a.N = N; a.K = K; a.ksplit = ksplit; a.ngroups = ngroups;
+    a.M = M; a.N = N; a.K = K; a.ksplit = ksplit; a.ngroups = ngroups; a.r_rows = r_rows;
     for (int g = 0; g < ngroups; g++) {
-        if (!A[g] || !B[g] || !C[g] || ((epilogue == G2_EPI_ADD || epilogue == G2_EPI_RELUSQ_BWD) && (!R || !R[g]))) return vrwkv_fail(VRWKV_EINVAL, "gemm2: null pointer (group %d)", g);
+        if (!A[g] || !B[g] || !C[g] || (need_r && (!R || !R[g])) || (need_b && !bias[g])) return vrwkv_fail(VRWKV_EINVAL, "gemm2: null pointer (group %d)", g);
         if ((((uintptr_t)A[g]) | ((uintptr_t)B[g]) | ((uintptr_t)C[g]) | (R ? (uintptr_t)R[g] : 0)) & 15)
             return vrwkv_fail(VRWKV_EINVAL, "gemm2: pointers must be 16-byte aligned");
         int rc;
@@ -393,6 +420,7 @@ extern "C" int vrwkv_gemm2_bf16_grouped(int M, int N, int K, int ngroups, const 
         a.C[g] = C[g];
         a.R[g] = R ? R[g] : nullptr;
         a.ct[g] = (c_transposed && c_transposed[g]) ? 1 : 0;
+        a.bias[g] = need_b ? bias[g] : nullptr;
         if (a.ct[g] && (epilogue != G2_EPI_NONE || ksplit > 1)) return vrwkv_fail(VRWKV_EINVAL, "gemm2: transposed store only with the plain epilogue");
     }
     for (int g = ngroups; g < G2_MAXG; g++) { maps.a[g] = maps.a[0]; maps.b[g] = maps.b[0]; }
@@ -413,6 +441,8 @@ extern "C" int vrwkv_gemm2_bf16_grouped(int M, int N, int K, int ngroups, const 
     G2_CASE(256, G2_EPI_RELUSQ_BWD, 0, 1)
     G2_LAYOUTS(128, G2_EPI_NONE) G2_LAYOUTS(128, G2_EPI_ADD) G2_LAYOUTS(128, G2_EPI_ATOMIC_F32) G2_CASE(128, G2_EPI_RELU_SQ, 0, 0)
     G2_CASE(128, G2_EPI_RELUSQ_BWD, 0, 1)
+    G2_CASE(256, G2_EPI_BIAS, 0, 0) G2_CASE(256, G2_EPI_BIAS_GELU, 0, 0) G2_CASE(256, G2_EPI_BIAS_ADD, 0, 0)
+    G2_CASE(128, G2_EPI_BIAS, 0, 0) G2_CASE(128, G2_EPI_BIAS_GELU, 0, 0) G2_CASE(128, G2_EPI_BIAS_ADD, 0, 0)
 #undef G2_LAYOUTS
 #undef G2_CASE
     return vrwkv_fail(VRWKV_EUNSUP, "gemm2: unsupported combination (layout %d, epilogue %d)", layout, epilogue);
@@ -420,5 +450,5 @@ extern "C" int vrwkv_gemm2_bf16_grouped(int M, int N, int K, int ngroups, const 
 
 extern "C" int vrwkv_gemm2_bf16(int M, int N, int K, const uint16_t* A, const uint16_t* B, uint16_t* C, int layout, int epilogue,
                                 const uint16_t* R, int ksplit, void* stream) {
-    return vrwkv_gemm2_bf16_grouped(M, N, K, 1, &A, &B, &C, &R, nullptr, layout, epilogue, ksplit, stream);
+    return vrwkv_gemm2_bf16_grouped(M, N, K, 1, &A, &B, &C, &R, nullptr, layout, epilogue, ksplit, nullptr, 0, stream);
 }

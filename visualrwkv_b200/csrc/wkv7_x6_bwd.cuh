@@ -1,7 +1,7 @@
 // wkv7_x6_bwd.cuh — WKV7 backward, round 2: one chunk-parallel kernel on the tcgen05 tensor cores ("x3" products:
 // two bf16 parts per operand, wkv7_x6_common.cuh).  Replaces the reference's serial reverse-time walk
 // (VisualRWKV-v7/v7.00/cuda/wkv7_cuda.cu:54-130) for callers that promise bounded decay; the algebra is the hand-derived
-// reverse pass of the chunk form (oracle/wkv7_chunked.py::chunk_backward, checked against the fp64 adjoint of the
+// reverse pass of the chunk form (the chunk_backward restatement kept with the tests, checked against the fp64 adjoint of the
 // step-by-step oracle):
 //     dZ = dS_L E_L                          [dU;dV] = [Bt;Kt] dZ^T + [A_qb|A_qk]^T dY        dR = (I - A_ab)^-T dU
 //     dS_0 = dZ + dR^T At + dY^T Qt          (the only quantity the previous chunk waits for)

@@ -1,7 +1,7 @@
 // wkv7_x6_fwd.cuh — WKV7 forward, round 2: chunk-parallel on the tcgen05 tensor cores at fp32-level accuracy.
 // Same operator contract as the reference forward_kernel (VisualRWKV-v7/v7.00/cuda/wkv7_cuda.cu:10-52): y (bf16),
 // sa (fp32, every step), s (fp32 transposed state checkpoints) — the algebra is the chunk-wise restatement kept with the
-// tests (oracle/wkv7_chunked.py), checked there against the step-by-step oracle.
+// tests (wkv7_chunked.py, test infrastructure), checked there against the step-by-step restatement of the reference.
 //
 // Work item = one 64-step chunk of one (batch, head).  A persistent grid (one 512-thread CTA per SM) takes items from an
 // atomic counter in chunk-major order (all (b,h) of chunk 0, then of chunk 1, ...).  Everything that does not depend on

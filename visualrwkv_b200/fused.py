@@ -474,14 +474,17 @@ def gemm_supported(M, N, K):
 G2_TN, G2_NN, G2_TT = 0, 2, 3     # layout bits: 1 = A stored [K,M], 2 = B stored [K,N]
 
 
-def gemm2_grouped(As, Bs, layout=G2_TN, epilogue=EPI_NONE, residuals=None, ksplit=1, transposed=None):
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_ADD = 5, 6, 7
+
+
+def gemm2_grouped(As, Bs, layout=G2_TN, epilogue=EPI_NONE, residuals=None, ksplit=1, transposed=None, biases=None, r_rows=0):
     """[epilogue(op(a) . op(b)) for a, b in zip(As, Bs)] in ONE launch (identical shapes), bf16 in / out, fp32 accumulate.
       G2_TN: a [M,K], b [N,K]  -> a @ b.T      (forward y = x W^T)
       G2_NN: a [M,K], b [K,N]  -> a @ b        (dgrad  dx = dy W)
       G2_TT: a [K,M], b [K,N]  -> a.T @ b      (wgrad  dW = dy^T x; ksplit > 1 slices the long contraction)"""
     L = _lib.lib()
     a, b = As[0], Bs[0]
-    _bf16c(*As, *Bs, *(residuals or []))
+    _bf16c(*As, *Bs, *(residuals or []), *(biases or []))
     a_mn, b_mn = layout & 1, (layout >> 1) & 1
     M, K = (a.shape[1], a.shape[0]) if a_mn else a.shape
     N = b.shape[1] if b_mn else b.shape[0]
@@ -490,12 +493,14 @@ def gemm2_grouped(As, Bs, layout=G2_TN, epilogue=EPI_NONE, residuals=None, kspli
     Cs = [torch.empty((N, M) if t else (M, N), dtype=torch.bfloat16, device=a.device) for t in tr]   # transposed[g]: C[g] = (a.b)^T
     _chk(L.vrwkv_gemm2_bf16_grouped(_c_int(M), _c_int(N), _c_int(K), _c_int(len(As)), _parr(As), _parr(Bs), _parr(Cs),
                                     _parr(residuals) if residuals else None, (_c_int * len(tr))(*tr), _c_int(layout), _c_int(epilogue),
-                                    _c_int(ksplit), _lib.cur_stream()), "vrwkv_gemm2_bf16_grouped")
+                                    _c_int(ksplit), _parr(biases) if biases else None, _c_int(r_rows), _lib.cur_stream()),
+         "vrwkv_gemm2_bf16_grouped")
     return Cs
 
 
-def gemm2(a, b, layout=G2_TN, epilogue=EPI_NONE, residual=None, ksplit=1):
-    return gemm2_grouped([a], [b], layout, epilogue, [residual] if residual is not None else None, ksplit)[0]
+def gemm2(a, b, layout=G2_TN, epilogue=EPI_NONE, residual=None, ksplit=1, bias=None, r_rows=0):
+    return gemm2_grouped([a], [b], layout, epilogue, [residual] if residual is not None else None, ksplit,
+                         biases=[bias] if bias is not None else None, r_rows=r_rows)[0]
 
 
 EPI_RELUSQ_BWD = 4
@@ -513,3 +518,37 @@ def _ksplit(groups, M, N, K):
     while ks < 8 and tiles * ks < 74 and K % (64 * ks * 2) == 0:
         ks *= 2
     return ks
+
+
+# ------------------------------------------------------------------------------------------------------
+# image -> language projector  (MLPWithContextGating, model.py:328-338; the LayerNorm after it is LayerNormFn)
+# ------------------------------------------------------------------------------------------------------
+class ProjectorFn(torch.autograd.Function):
+    """(x [rows, Dv], gate.weight [Dv, Dv], o_proj.weight [C, Dv]) -> o_proj(x * sigmoid(gate(x))) [rows, C]."""
+
+    @staticmethod
+    def forward(ctx, x, Wg, Wo):
+        L = _lib.lib()
+        g = gemm2(x, Wg)
+        h = torch.empty_like(x)
+        _chk(L.vrwkv_sigmul_forward(_c_size_t(x.numel()), _p(x), _p(g), _p(h), _lib.cur_stream()), "vrwkv_sigmul_forward")
+        o = gemm2(h, Wo)
+        ctx.save_for_backward(x, g, h, Wg, Wo)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        L = _lib.lib()
+        x, g, h, Wg, Wo = ctx.saved_tensors
+        rows, Dv = x.shape
+        C = Wo.shape[0]
+        do = do.contiguous()
+        dh = gemm2(do, Wo, G2_NN)
+        dWo = gemm2(do, h, G2_TT, ksplit=_ksplit(1, C, Dv, rows))
+        need_dx = ctx.needs_input_grad[0]
+        dx1 = torch.empty_like(x) if need_dx else None
+        dg = torch.empty_like(x)
+        _chk(L.vrwkv_sigmul_backward(_c_size_t(x.numel()), _p(x), _p(g), _p(dh), _p(dx1), _p(dg), _lib.cur_stream()), "vrwkv_sigmul_backward")
+        dWg = gemm2(dg, x, G2_TT, ksplit=_ksplit(1, Dv, Dv, rows))
+        dx = gemm2(dg, Wg, G2_NN, EPI_ADD, dx1) if need_dx else None
+        return dx, dWg, dWo

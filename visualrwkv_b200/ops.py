@@ -6,12 +6,13 @@ There is no CPU / eager fallback here: CUDA bf16 tensors are required and the na
 """
 from __future__ import annotations
 
+import ctypes
 import warnings
 
 import torch
 import torch.nn.functional as F
 
-from . import fused
+from . import _lib, fused
 
 
 def _need_cuda_bf16(x, what):
@@ -65,36 +66,84 @@ def block_forward(blk, x, v_first):
 def projector_forward(m, x):
     """MLPWithContextGating.forward (model.py:335-338): LN(o_proj(x * sigmoid(gate(x))))."""
     _need_cuda_bf16(x, "MLPWithContextGating")
+    shp = x.shape
+    x2 = x.reshape(-1, shp[-1]).contiguous()
+    rows, Dv = x2.shape
+    C = m.o_proj.weight.shape[0]
+    if fused.gemm2_supported(rows, Dv, Dv) and fused.gemm2_supported(rows, C, Dv) and fused.gemm2_supported(Dv, Dv, rows) and \
+            fused.gemm2_supported(C, Dv, rows) and fused.gemm2_supported(rows, Dv, C):
+        o = fused.ProjectorFn.apply(x2, m.gate.weight, m.o_proj.weight)    # CTA-pair GEMMs + the gate kernel, hand-written backward
+        return layer_norm(o.view(*shp[:-1], C), m.ln_v)
     gating = torch.sigmoid(m.gate(x))
     return layer_norm(m.o_proj(x * gating), m.ln_v)
 
 
 def adaptive_pooling(feats, out_hw):
-    """VisualRWKV.adaptive_pooling (model.py:442-447): [N,L,D] -> [N,out_hw^2,D]."""
+    """VisualRWKV.adaptive_pooling (model.py:442-447): [N,L,D] -> [N,out_hw^2,D] (csrc/glue.cu; the tower is frozen and
+    detached, so there is no backward)."""
     N, L, D = feats.shape
     hw = int(L ** 0.5)
     if hw == out_hw:
         return feats
-    f = feats.view(N, hw, hw, D).permute(0, 3, 1, 2)
-    f = F.adaptive_avg_pool2d(f, out_hw)
-    return f.reshape(N, D, -1).permute(0, 2, 1).contiguous()
+    if not (feats.is_cuda and feats.dtype == torch.bfloat16 and D % 8 == 0) or feats.requires_grad:
+        f = feats.view(N, hw, hw, D).permute(0, 3, 1, 2)
+        f = F.adaptive_avg_pool2d(f, out_hw)
+        return f.reshape(N, D, -1).permute(0, 2, 1).contiguous()
+    x = feats.contiguous()
+    y = torch.empty(N, out_hw * out_hw, D, dtype=x.dtype, device=x.device)
+    fused._chk(_lib.lib().vrwkv_adaptive_pool(N, hw, out_hw, D, fused._p(x), fused._p(y), _lib.cur_stream()), "vrwkv_adaptive_pool")
+    return y
 
 
-_pending_count = None  # (event, pinned count tensor, n_features, sample_ids) of the previous call
+class _PendingCount:
+    """Deferred image-token count check of one embed_and_scatter call (per call, not module state: re-entrant across
+    models / streams)."""
+
+    def __init__(self, event, host, n_feat, sample_ids):
+        self.event, self.host, self.n_feat, self.sample_ids = event, host, n_feat, sample_ids
+
+    def check(self):
+        self.event.synchronize()
+        n_sel = int(self.host)
+        if n_sel != self.n_feat:
+            warnings.warn(f"sample_id: {':::'.join(self.sample_ids or [])}, image tokens: {n_sel}, but image features: {self.n_feat}")
+        if n_sel > self.n_feat:
+            raise RuntimeError(f"{n_sel} image-token slots but only {self.n_feat} image feature rows (model.py:487-493)")
 
 
-def _check_pending_count():
-    global _pending_count
-    if _pending_count is None:
-        return
-    ev, host, n_feat, sample_ids = _pending_count
-    _pending_count = None
-    ev.synchronize()
-    n_sel = int(host)
-    if n_sel != n_feat:
-        warnings.warn(f"sample_id: {':::'.join(sample_ids or [])}, image tokens: {n_sel}, but image features: {n_feat}")
-    if n_sel > n_feat:
-        raise RuntimeError(f"{n_sel} image-token slots but only {n_feat} image feature rows (model.py:487-493)")
+_pending = []  # checks not yet looked at (drained by the next call on any model and by flush_checks())
+
+
+def _drain_pending():
+    while _pending:
+        _pending.pop(0).check()
+
+
+class EmbedScatterFn(torch.autograd.Function):
+    """(emb table [V,D], ids [B,L] int64, features [F,D]) -> [B,L,D]; gradient to the features only (frozen table)."""
+
+    @staticmethod
+    def forward(ctx, emb_weight, input_ids, feats, image_token_index, count_dev):
+        B, L = input_ids.shape
+        D = emb_weight.shape[1]
+        ids = input_ids.contiguous()
+        out = torch.empty(B * L, D, dtype=emb_weight.dtype, device=emb_weight.device)
+        fused._chk(_lib.lib().vrwkv_embed_scatter_forward(B * L, D, feats.shape[0], ctypes.c_longlong(image_token_index), fused._p(ids),
+                                                          fused._p(emb_weight), fused._p(feats), fused._p(out), fused._p(count_dev),
+                                                          _lib.cur_stream()), "vrwkv_embed_scatter_forward")
+        ctx.save_for_backward(ids)
+        ctx.meta = (B * L, D, feats.shape[0], image_token_index)
+        return out.view(B, L, D)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ids,) = ctx.saved_tensors
+        ntok, D, nfeat, idx = ctx.meta
+        do = dout.reshape(ntok, D).contiguous()
+        dfeats = torch.empty(nfeat, D, dtype=do.dtype, device=do.device)
+        fused._chk(_lib.lib().vrwkv_embed_scatter_backward(ntok, D, nfeat, ctypes.c_longlong(idx), fused._p(ids), fused._p(do), fused._p(dfeats),
+                                                           _lib.cur_stream()), "vrwkv_embed_scatter_backward")
+        return None, None, dfeats, None, None
 
 
 def embed_and_scatter(emb_weight, input_ids, image_features, image_token_index, sample_ids=None):
@@ -102,38 +151,42 @@ def embed_and_scatter(emb_weight, input_ids, image_features, image_token_index, 
     image features in row-major order of appearance (bit-exact copy; gradient flows to the features).  Surplus
     feature rows are dropped like the reference's `image_features[:selected.sum()]` (:487-491).
 
-    The reference reads `selected.sum()` on the host every step (a device synchronisation in the middle of the
-    forward).  Here the k-th selected row gathers feature row k on the device, and the count travels
-    to pinned host memory asynchronously: the reference's mismatch warning (and an error when there are more slots
-    than features) is raised at the next call / `flush_checks()` instead of stalling this one."""
-    global _pending_count
-    _check_pending_count()
+    One kernel (csrc/glue.cu) instead of embedding + cumsum + index_select + where.  The reference reads
+    `selected.sum()` on the host every step (a device synchronisation in the middle of the forward, SURVEY.md §8 a12);
+    here the count travels to pinned host memory asynchronously and the reference's mismatch warning (an error when
+    there are more slots than features) is raised at the next call / `flush_checks()` instead of stalling this one."""
+    _drain_pending()
     B, L = input_ids.shape
     D = emb_weight.shape[1]
-    x = F.embedding(input_ids, emb_weight).view(B * L, D)
-    sel = input_ids.view(-1) == image_token_index
-    feats = image_features.reshape(-1, D).to(x.dtype)
-    rank = torch.cumsum(sel, dim=0, dtype=torch.int32) - 1          # k for the k-th selected row
-    if feats.shape[0] == 0:
-        return x.view(B, L, D)
-    gathered = feats.index_select(0, rank.clamp(0, feats.shape[0] - 1).to(torch.int64))
-    x = torch.where(sel.unsqueeze(-1), gathered, x)
-    if input_ids.is_cuda:
-        host = torch.empty((), dtype=torch.int32, pin_memory=True)
-        host.copy_(rank[-1] + 1, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        _pending_count = (ev, host, feats.shape[0], sample_ids)
-    else:
+    feats = image_features.reshape(-1, D).to(emb_weight.dtype)
+    on_gpu = input_ids.is_cuda and emb_weight.dtype == torch.bfloat16 and D % 8 == 0 and not emb_weight.requires_grad
+    if not on_gpu:   # CPU / trainable-table path (tests of the host logic): eager
+        x = F.embedding(input_ids, emb_weight).view(B * L, D)
+        sel = input_ids.view(-1) == image_token_index
+        rank = torch.cumsum(sel, dim=0, dtype=torch.int32) - 1
+        if feats.shape[0] > 0:
+            gathered = feats.index_select(0, rank.clamp(0, feats.shape[0] - 1).to(torch.int64))
+            x = torch.where(sel.unsqueeze(-1), gathered, x)
         n_sel = int(rank[-1]) + 1
         if n_sel != feats.shape[0]:
             warnings.warn(f"sample_id: {':::'.join(sample_ids or [])}, image tokens: {n_sel}, but image features: {feats.shape[0]}")
-    return x.view(B, L, D)
+        if n_sel > feats.shape[0]:
+            raise RuntimeError(f"{n_sel} image-token slots but only {feats.shape[0]} image feature rows (model.py:487-493)")
+        return x.view(B, L, D)
+    count_dev = torch.empty((), dtype=torch.int32, device=input_ids.device)
+    out = EmbedScatterFn.apply(emb_weight, input_ids, feats.contiguous(), int(image_token_index), count_dev)
+    if not torch.cuda.is_current_stream_capturing():
+        host = torch.empty((), dtype=torch.int32, pin_memory=True)
+        host.copy_(count_dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        _pending.append(_PendingCount(ev, host, feats.shape[0], sample_ids))
+    return out
 
 
 def flush_checks():
-    """Raise / warn now for the deferred image-token count check of the last embed_and_scatter call."""
-    _check_pending_count()
+    """Raise / warn now for the deferred image-token count checks of earlier embed_and_scatter calls."""
+    _drain_pending()
 
 
 def training_loss(logits, targets, ignore_index, l2wrap):
