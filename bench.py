@@ -37,7 +37,7 @@ WKV_BWD_BYTES_PER_ELEM = 26  # 7 bf16 reads + 6 bf16 writes
 # (B8 T2048 C768) from the ncu --set full captures named beside them (profiles/); None = not captured for this build.
 WKV_PATHS = {
     "x6": {"fwd": "wkv7_x6_fwd_kernel<chunk checkpoints>", "bwd": "wkv7_x3_bwd_kernel",
-           "traffic_fwd": int((151.093 + 84.057) * 1e6), "traffic_bwd": None, "ncu": "profiles/r2_wkv7_x6_summary.csv"},
+           "traffic_fwd": int((151.093 + 84.057) * 1e6), "traffic_bwd": int((275.737 + 126.352) * 1e6), "ncu": "profiles/r2_ncu_summary.csv"},
     "step": {"fwd": "wkv7_fwd2_kernel<4,4>", "bwd": "wkv7_bwd2_kernel<4,3>", "traffic_fwd": int((151 + 226) * 1e6), "traffic_bwd": None,
              "ncu": "profiles/r1b_*"},
     "tf32": {"fwd": "wkv7_chunk_fwd_kernel<chunk checkpoints>", "bwd": "wkv7_chunk_dstate_kernel + wkv7_chunk_bwd_kernel",
