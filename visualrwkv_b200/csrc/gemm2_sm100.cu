@@ -28,6 +28,7 @@
 // Operand tiles are bf16 64x64 boxes (8 KB, SWIZZLE_128B): K-major operands take [rows][64 k] boxes, MN-major operands
 // [64 k-lines][64 m/n] boxes — the same TMA box shape, only the UMMA descriptor differs (umma.cuh).
 #include <cudaTypedefs.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "host_util.h"
@@ -50,11 +51,14 @@ struct Gemm2Args {
     int ct[G2_MAXG];             // 1: store this group's result transposed (C[g] is [N,M]); EPI_NONE only
     const uint16_t* bias[G2_MAXG];  // [N] (EPI_BIAS*)
     int r_rows;                  // rows of R (EPI_BIAS_ADD: R row = row % r_rows — a position table shared by all images); 0 = M
+    int dbg_mode;                // development (VRWKV_GEMM2_DBG): 1 = no TMA traffic after the ring is primed (results wrong: tensor-core
+                                 // ceiling), 2 = no MMAs (load ceiling)
     float* Cf;          // ATOMIC_F32: fp32 partial sums [ngroups][M][N]; must be zero on entry, is zero again on exit
     int* tickets;       // ATOMIC_F32: one counter per (group, tile, CTA of the pair); zero on entry and on exit
 };
 struct Gemm2Maps {
     CUtensorMap a[G2_MAXG], b[G2_MAXG];
+    CUtensorMap c[G2_MAXG];   // C as [M rows][N cols], box [32 rows][64 cols], SWIZZLE_128B: the epilogue's TMA stores
 };
 
 __device__ __forceinline__ bool g2_elect() {
@@ -102,6 +106,7 @@ template <int BN, int STAGES>
 struct alignas(1024) Gemm2Smem {
     uint8_t a[STAGES][G2_BM * G2_BK * 2];         // 16 KB per stage: this CTA's 128 rows of A (two 8 KB boxes when MN-major)
     uint8_t b[STAGES][(BN / 2) * G2_BK * 2];      // this CTA's half of the B tile
+    uint8_t stg[8][2][4096];                      // per epilogue warp: two [32 rows][64 cols] bf16 staging tiles for the TMA stores
     uint64_t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
 };
@@ -109,7 +114,7 @@ struct alignas(1024) Gemm2Smem {
 template <int BN, int EPI, int A_MN, int B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
-    constexpr int STAGES = (BN == 256) ? 6 : 8;
+    constexpr int STAGES = (BN == 256) ? 5 : 6;
     constexpr int NACC = 2;
     constexpr uint32_t STAGE_BYTES = G2_BM * G2_BK * 2 + (BN / 2) * G2_BK * 2;
     extern __shared__ __align__(1024) uint8_t g2_smem[];
@@ -160,6 +165,10 @@ gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
                 for (int kb = 0; kb < nkb; kb++, it++) {
                     const int s = it % STAGES, k0 = (ks * nkb + kb) * G2_BK;
                     if (it >= STAGES) mbar_wait(&sm.empty[s], ((it / STAGES) - 1) & 1);
+                    if (p.dbg_mode == 1 && it >= STAGES) {
+                        if (leader) mbar_arrive(&sm.full[s]);
+                        continue;
+                    }
                     if (leader) mbar_arrive_expect_tx(&sm.full[s], 2 * STAGE_BYTES);
                     if (A_MN) {
                         tma_load_2d_pair(&sm.a[s][0], tm_a_, m0, k0, &sm.full[s]);
@@ -195,6 +204,7 @@ gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
                     const uint32_t oa = (uint32_t)(&sm.a[s][0] - (uint8_t*)&sm), ob = (uint32_t)(&sm.b[s][0] - (uint8_t*)&sm);
 #pragma unroll
                     for (int k = 0; k < G2_BK / 16; k++) {
+                        if (p.dbg_mode == 2) break;
                         const uint64_t da = A_MN ? bdesc_mn(b4, oa + k * 2048) : bdesc_k(b4, oa + k * 32);
                         const uint64_t db = B_MN ? bdesc_mn(b4, ob + k * 2048) : bdesc_k(b4, ob + k * 32);
                         umma_bf16_pair(tc, da, db, idesc, (kb | k) != 0);
@@ -219,11 +229,24 @@ gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
             float* const Cfg = (EPI == G2_EPI_ATOMIC_F32) ? p.Cf + (size_t)g * p.M * p.N : nullptr;
             mbar_wait(&sm.tmem_full[acc], (lt / NACC) & 1);
             tc_fence_after();
+            // Plain results leave through shared memory and TMA stores (full 128-byte lines per row): 32 lanes writing 16 bytes
+            // to 32 different rows each cost one L2 transaction per lane and held the epilogue at ~12 k cycles per tile — twice
+            // the tensor-core time of a K = 768 tile.  The atomic (split-K) and transposed epilogues keep register stores.
+            const bool via_tma = EPI != G2_EPI_ATOMIC_F32 && !(EPI == G2_EPI_NONE && p.ct[g]);
+            int chunk_i = 0;
 #pragma unroll 1
-            for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+            for (int c64 = half * (BN / 2); c64 < (half + 1) * (BN / 2); c64 += 64, chunk_i++) {
+                uint8_t* const stile = &sm.stg[warp - 2][chunk_i & 1][0];
+                if (via_tma) {
+                    if (g2_elect()) tma_store_wait_read<1>();   // the store that read this staging tile two chunks ago is done
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int sub = 0; sub < 2; sub++) {
+                const int c = c64 + 32 * sub;
                 uint32_t r[32];
                 tmem_ld32(tmem_c + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN + c), r);
-                if (row < p.M) {
+                if (row < p.M || via_tma) {
                     const size_t off = (size_t)row * p.N + n0 + c;
                     if (EPI == G2_EPI_ATOMIC_F32) {
 #pragma unroll
@@ -235,9 +258,10 @@ gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
                         uint4 out[4], res[4];
                         uint32_t* o = reinterpret_cast<uint32_t*>(out);
                         uint4 bia[4];
+                        const bool inb = row < p.M;
                         if (EPI == G2_EPI_ADD || EPI == G2_EPI_RELUSQ_BWD) {
 #pragma unroll
-                            for (int i = 0; i < 4; i++) res[i] = *reinterpret_cast<const uint4*>(Rg + off + 8 * i);
+                            for (int i = 0; i < 4; i++) res[i] = inb ? *reinterpret_cast<const uint4*>(Rg + off + 8 * i) : make_uint4(0u, 0u, 0u, 0u);
                         }
                         if (EPI == G2_EPI_BIAS || EPI == G2_EPI_BIAS_GELU || EPI == G2_EPI_BIAS_ADD) {
 #pragma unroll
@@ -245,7 +269,7 @@ gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
                             if (EPI == G2_EPI_BIAS_ADD) {
                                 const size_t roff = (size_t)(p.r_rows ? row % p.r_rows : row) * p.N + n0 + c;
 #pragma unroll
-                                for (int i = 0; i < 4; i++) res[i] = *reinterpret_cast<const uint4*>(Rg + roff + 8 * i);
+                                for (int i = 0; i < 4; i++) res[i] = inb ? *reinterpret_cast<const uint4*>(Rg + roff + 8 * i) : make_uint4(0u, 0u, 0u, 0u);
                             }
                         }
                         const uint32_t* bb = reinterpret_cast<const uint32_t*>(bia);
@@ -280,16 +304,30 @@ gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
                             }
                             o[i] = pack_bf16x2(x0, x1);
                         }
-                        if (EPI == G2_EPI_NONE && p.ct[g]) {
+                        if (!via_tma) {
                             // C^T: lanes hold consecutive rows, so each of the 32 columns is one 64-byte run across the warp
                             const uint16_t* o16 = reinterpret_cast<const uint16_t*>(out);
+                            if (inb) {
 #pragma unroll
-                            for (int i = 0; i < 32; i++) Cg[(size_t)(n0 + c + i) * p.M + row] = o16[i];
+                                for (int i = 0; i < 32; i++) Cg[(size_t)(n0 + c + i) * p.M + row] = o16[i];
+                            }
                         } else {
+                            // staging tile row = lane, 128 bytes (64 columns), 16-byte chunks XOR-swizzled by (row & 7)
 #pragma unroll
-                            for (int i = 0; i < 4; i++) *reinterpret_cast<uint4*>(Cg + off + 8 * i) = out[i];
+                            for (int i = 0; i < 4; i++)
+                                *reinterpret_cast<uint4*>(stile + lane * 128 + (((4 * sub + i) ^ (lane & 7)) << 4)) = out[i];
                         }
                     }
+                }
+                }
+                if (via_tma) {
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (g2_elect()) {
+                        tma_store_2d(&maps.c[g], stile, n0 + c64, m0 + 32 * q);
+                        tma_store_commit();
+                    }
+                    __syncwarp();
                 }
             }
             if (EPI == G2_EPI_ATOMIC_F32) {
@@ -322,6 +360,8 @@ gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(&sm.tmem_empty[acc], 0);   // the leader's MMA warp waits for all 8 epilogue warps
         }
+        if (g2_elect()) tma_store_wait<0>();   // this warp's bulk stores have landed before the CTA (and its shared memory) goes away
+        __syncwarp();
     }
     tc_fence_before();
     cluster_sync_all();   // nobody leaves (or frees TMEM) while the partner may still signal / be read
@@ -338,7 +378,7 @@ using namespace vrwkv;
 template <int BN, int EPI, int A_MN, int B_MN>
 static int launch_gemm2(const Gemm2Maps& maps, const Gemm2Args& a, cudaStream_t st) {
     auto kern = gemm2_kernel<BN, EPI, A_MN, B_MN>;
-    constexpr int STAGES = (BN == 256) ? 6 : 8;
+    constexpr int STAGES = (BN == 256) ? 5 : 6;
     const size_t smem = sizeof(Gemm2Smem<BN, STAGES>) + 1024;
     VRWKV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int nwork = a.ngroups * (a.N / BN) * ((a.M + 2 * G2_BM - 1) / (2 * G2_BM)) * a.ksplit;
@@ -405,6 +445,10 @@ extern "C" int vrwkv_gemm2_bf16_grouped(int M, int N, int K, int ngroups, const 
     Gemm2Maps maps;
     Gemm2Args a{};
     a.M = M; a.N = N; a.K = K; a.ksplit = ksplit; a.ngroups = ngroups; a.r_rows = r_rows;
+    {
+        static const int dbg = [] { const char* e = getenv("VRWKV_GEMM2_DBG"); return e ? atoi(e) : 0; }();
+        a.dbg_mode = dbg;
+    }
     for (int g = 0; g < ngroups; g++) {
         if (!A[g] || !B[g] || !C[g] || (need_r && (!R || !R[g])) || (need_b && !bias[g])) return vrwkv_fail(VRWKV_EINVAL, "gemm2: null pointer (group %d)", g);
         if ((((uintptr_t)A[g]) | ((uintptr_t)B[g]) | ((uintptr_t)C[g]) | (R ? (uintptr_t)R[g] : 0)) & 15)
@@ -417,13 +461,17 @@ extern "C" int vrwkv_gemm2_bf16_grouped(int M, int N, int K, int ngroups, const 
         if (b_mn) rc = vrwkv_encode_2d(&maps.b[g], B[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)N, (uint64_t)K, (uint64_t)N * 2, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
         else rc = vrwkv_encode_2d(&maps.b[g], B[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, G2_BK, BN / 2, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
+        const bool transposed = c_transposed && c_transposed[g];
+        if ((rc = vrwkv_encode_2d(&maps.c[g], C[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, transposed ? (uint64_t)M : (uint64_t)N,
+                                  transposed ? (uint64_t)N : (uint64_t)M, (transposed ? (uint64_t)M : (uint64_t)N) * 2, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B)))
+            return rc;
         a.C[g] = C[g];
         a.R[g] = R ? R[g] : nullptr;
         a.ct[g] = (c_transposed && c_transposed[g]) ? 1 : 0;
         a.bias[g] = need_b ? bias[g] : nullptr;
         if (a.ct[g] && (epilogue != G2_EPI_NONE || ksplit > 1)) return vrwkv_fail(VRWKV_EINVAL, "gemm2: transposed store only with the plain epilogue");
     }
-    for (int g = ngroups; g < G2_MAXG; g++) { maps.a[g] = maps.a[0]; maps.b[g] = maps.b[0]; }
+    for (int g = ngroups; g < G2_MAXG; g++) { maps.a[g] = maps.a[0]; maps.b[g] = maps.b[0]; maps.c[g] = maps.c[0]; }
     int epi = epilogue;
     if (ksplit > 1) {
         epi = G2_EPI_ATOMIC_F32;
