@@ -155,6 +155,8 @@ def main():
     ap.add_argument("--wkv", default="x6", choices=sorted(WKV_PATHS),
                     help="WKV7 kernels of the time-mix block: x6 (default; chunked tensor-core kernels at fp32-level accuracy, pass the "
                          "strict parity tests), step (step-by-step fp32 kernels), tf32 (round-1 kernels, outside the tolerance)")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the step as one CUDA graph (visualrwkv_b200.graph.GraphedTrainStep); auto = on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-kernel", action="store_true")
     ap.add_argument("--grad-cp", type=int, default=0)
@@ -213,7 +215,9 @@ def main():
     master = [p.detach().float().clone() for p in trainable]
     for mp in master:
         mp.grad = torch.zeros_like(mp)
-    opt = torch.optim.AdamW(master, lr=1e-5, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.0, fused=True)
+    use_graph = a.graph != "off"
+    opt = torch.optim.AdamW(master, lr=torch.tensor(1e-5, device=dev) if use_graph else 1e-5, betas=(0.9, 0.99), eps=1e-8,
+                            weight_decay=0.0, fused=True, capturable=use_graph)
 
     B, T = a.batch, a.ctx
     host = make_batch(B, T, 576, 224, seed=100 + rank, img_dtype=torch.bfloat16)
@@ -221,7 +225,15 @@ def main():
     resident = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
 
-    def train_step(batch):
+    def apply_grads():
+        if reducer is not None:
+            reducer.finish()
+        with torch.no_grad():
+            torch._foreach_copy_([m.grad for m in master], [p.grad for p in trainable])
+            opt.step()
+            torch._foreach_copy_(trainable, master)
+
+    def eager_step(batch):
         if reducer is not None:
             reducer.reset()
         else:
@@ -229,18 +241,32 @@ def main():
                 p.grad = None
         loss = model.training_step(batch)
         loss.backward()
-        if reducer is not None:
-            reducer.finish()
-        with torch.no_grad():
-            torch._foreach_copy_([m.grad for m in master], [p.grad for p in trainable])
-            opt.step()
-            torch._foreach_copy_(trainable, master)
+        apply_grads()
         return loss
 
+    train_step = eager_step
+    graph_note = "eager launches"
+    if use_graph:
+        try:
+            from visualrwkv_b200.graph import GraphedTrainStep
+            gstep = GraphedTrainStep(model, resident, after_backward=apply_grads, before_forward=(reducer.reset if reducer is not None else None),
+                                     set_grads_to_none=reducer is None)
+            train_step = gstep
+            graph_note = "one CUDA graph per step (forward + backward + grad all-reduce + AdamW)"
+        except Exception as e:  # noqa: BLE001
+            if a.graph == "on":
+                raise
+            graph_note = f"eager launches (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
+            torch.cuda.synchronize()
+    config["launch"] = graph_note
+
     def e2e_step():
-        batch = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
-        loss = train_step(batch)
-        return float(loss)  # D2H read of the loss (synchronises)
+        if train_step is not eager_step:
+            loss = train_step(host)   # the graphed step copies the pinned host tensors into its static device buffers (H2D)
+        else:
+            batch = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
+            loss = train_step(batch)
+        return float(loss.detach())  # D2H read of the loss (synchronises)
 
     def barrier():
         if world > 1:
@@ -260,14 +286,28 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps
 
+    graphed = train_step is not eager_step
     for _ in range(max(a.warmup, 3)):
         train_step(resident)
-    wkv7.PROFILE = []
+    if not graphed:
+        wkv7.PROFILE = []
     lc0 = wkv7.launch_count()
     with ClockSampler(local_rank) as cs:
         ms = timed(lambda: train_step(resident), a.steps)
     launches = wkv7.launch_count() - lc0
+    if graphed:
+        # a replayed graph does not pass through the host-side launch counter, and CUDA events cannot time single kernels
+        # inside it: count the launches of ONE eager replica of the step and time the WKV7 kernels there (same kernels,
+        # same shapes, same buffers), right after the timed region
+        torch.cuda.synchronize()
+        eager_step(resident)
+        wkv7.PROFILE = []
+        lc0 = wkv7.launch_count()
+        eager_step(resident)
+        eager_step(resident)
+        launches = (wkv7.launch_count() - lc0) // 2 * a.steps
     prof, wkv7.PROFILE = wkv7.PROFILE, None
+    prof_steps = 2 if graphed else a.steps
     torch.cuda.synchronize()
     ms_e2e = timed(e2e_step, a.steps)
 
@@ -295,12 +335,13 @@ def main():
                                 "peak": peak, "unit": "GB/s", "frac": WKV_BWD_BYTES_PER_ELEM * nel / bms / 1e6 / peak,
                                 "traffic": wp["traffic_bwd"] if at_cfg2 else None, "traffic_unit": "bytes", "traffic_source": wp["ncu"],
                                 "avg_launch_ms": bms, "launches_timed": len(bwd),
-                                "peak_source": peaks["source"], "share_of_step": sum(bwd) / a.steps / ms}
+                                "peak_source": peaks["source"], "share_of_step": sum(bwd) / prof_steps / ms,
+                                "timed_in": "eager replica of the step right after the timed region (the timed region replays one CUDA graph)" if graphed else "the timed region"}
             line["roofline_wkv7_fwd"] = {"kernel": wp["fwd"], "bound": "hbm", "achieved": WKV_FWD_BYTES_PER_ELEM * nel / fms / 1e6,
                                          "peak": peak, "unit": "GB/s", "frac": WKV_FWD_BYTES_PER_ELEM * nel / fms / 1e6 / peak,
                                          "traffic": wp["traffic_fwd"] if at_cfg2 else None,
                                          "traffic_unit": "bytes", "avg_launch_ms": fms, "launches_timed": len(fwd),
-                                         "share_of_step": sum(fwd) / a.steps / ms}
+                                         "share_of_step": sum(fwd) / prof_steps / ms}
         # model FLOPs (GEMMs only): fwd 281 MFLOP/token at 0.1B -> x3 for fwd+bwd
         C, L, V = args.n_embd, args.n_layer, args.vocab_size
         lora = LORA_RANKS.get(C, 0)

@@ -202,3 +202,36 @@ def test_bench_line_keys():
     r = d["roofline"]
     assert r["bound"] == "hbm" and 0 < r["frac"] < 1 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert "x3_bwd" in r["kernel"] and d["config"]["wkv"] == "x6"  # default: the chunked kernels that pass the strict parity tests
+
+
+def test_graphed_train_step_matches_eager():
+    """visualrwkv_b200.graph.GraphedTrainStep: the whole step replayed as one CUDA graph (native kernels, their
+    stream-ordered workspaces and the flag-chained WKV7 kernels included) gives the eager step's loss and gradients."""
+    from visualrwkv_b200.graph import GraphedTrainStep
+    from visualrwkv_b200.model import VisualRWKV, default_args, randomize_zero_init
+    torch.manual_seed(0)
+    args = default_args(n_embd=128, n_layer=2, dim_att=128, vision_tower_path="siglip-tiny-test", num_token_per_image=16, ctx_len=128)
+    model = VisualRWKV(args)
+    randomize_zero_init(model)
+    model = model.to(device="cuda", dtype=torch.bfloat16)
+    model.freeze_emb()
+    b1 = MR.make_batch(2, 128, 16, 64, seed=1, device="cuda", img_dtype=torch.bfloat16)
+    b2 = MR.make_batch(2, 128, 16, 64, seed=2, device="cuda", img_dtype=torch.bfloat16)
+
+    def eager(batch):
+        for p in model.parameters():
+            p.grad = None
+        loss = model.training_step(batch)
+        loss.backward()
+        return float(loss), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    l1, g1 = eager(b1)
+    l2, g2 = eager(b2)
+    step = GraphedTrainStep(model, b1)
+    for batch, lref, gref in ((b1, l1, g1), (b2, l2, g2), (b1, l1, g1)):
+        loss = step(batch)
+        torch.cuda.synchronize()
+        assert abs(float(loss) - lref) < 1e-3 * max(1.0, abs(lref))
+        for n, p in model.named_parameters():
+            if n in gref:
+                assert _rel(p.grad, gref[n]) < 1e-3 or float(gref[n].float().abs().max()) == 0.0, n

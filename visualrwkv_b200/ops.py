@@ -155,7 +155,8 @@ def embed_and_scatter(emb_weight, input_ids, image_features, image_token_index, 
     `selected.sum()` on the host every step (a device synchronisation in the middle of the forward, SURVEY.md §8 a12);
     here the count travels to pinned host memory asynchronously and the reference's mismatch warning (an error when
     there are more slots than features) is raised at the next call / `flush_checks()` instead of stalling this one."""
-    _drain_pending()
+    if not (input_ids.is_cuda and torch.cuda.is_current_stream_capturing()):
+        _drain_pending()
     B, L = input_ids.shape
     D = emb_weight.shape[1]
     feats = image_features.reshape(-1, D).to(emb_weight.dtype)
