@@ -225,13 +225,16 @@ def main():
     resident = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
 
-    def apply_grads():
-        if reducer is not None:
-            reducer.finish()
+    def apply_grads_local():
         with torch.no_grad():
             torch._foreach_copy_([m.grad for m in master], [p.grad for p in trainable])
             opt.step()
             torch._foreach_copy_(trainable, master)
+
+    def apply_grads():
+        if reducer is not None:
+            reducer.finish()
+        apply_grads_local()
 
     def eager_step(batch):
         if reducer is not None:
@@ -249,14 +252,41 @@ def main():
     if use_graph:
         try:
             from visualrwkv_b200.graph import GraphedTrainStep
-            gstep = GraphedTrainStep(model, resident, after_backward=apply_grads, before_forward=(reducer.reset if reducer is not None else None),
-                                     set_grads_to_none=reducer is None)
-            train_step = gstep
-            graph_note = "one CUDA graph per step (forward + backward + grad all-reduce + AdamW)"
+            if reducer is None:
+                gstep = GraphedTrainStep(model, resident, after_backward=apply_grads)
+                train_step = gstep
+                graph_note = "one CUDA graph per step (forward + backward + AdamW)"
+            else:
+                # collectives stay outside the graphs (NCCL inside a capture hung on this stack): graph 1 = forward + backward into
+                # the flat gradient buckets, then one NCCL all-reduce per bucket, then graph 2 = master copy + AdamW + copy back
+                reducer.overlap = False
+                gstep = GraphedTrainStep(model, resident, before_forward=reducer.zero_buckets, set_grads_to_none=False)
+                opt_graph = torch.cuda.CUDAGraph()
+                reducer.allreduce_all()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    apply_grads_local()
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                with torch.cuda.graph(opt_graph):
+                    apply_grads_local()
+
+                def graphed_ddp_step(batch):
+                    loss = gstep(batch)
+                    reducer.allreduce_all()
+                    opt_graph.replay()
+                    return loss
+
+                train_step = graphed_ddp_step
+                graph_note = "CUDA graph (forward + backward) + NCCL all-reduce per bucket + CUDA graph (AdamW)"
         except Exception as e:  # noqa: BLE001
             if a.graph == "on":
                 raise
             graph_note = f"eager launches (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
+            if reducer is not None:
+                reducer.overlap = True
+            train_step = eager_step
             torch.cuda.synchronize()
     config["launch"] = graph_note
 

@@ -141,6 +141,24 @@ def test_ddp_bucket_reducer_gloo_world2(tmp_path):
         for p, g0, g1 in zip(net.parameters(), *grads):
             if p.requires_grad:
                 assert torch.allclose(p.grad, (g0 + g1) / 2, atol=1e-6), "bucketed all-reduce mismatch"
+        # hook-free mode (what the CUDA-graphed step uses: collectives outside the graph) + the set_to_none guard
+        red.overlap = False
+        for p in net.parameters():
+            p.grad = None                      # what optimizer.zero_grad(set_to_none=True) does: reset() must re-attach the views
+        red.reset()
+        red.zero_buckets()
+        x = torch.randn(5, 16, generator=torch.Generator().manual_seed(100 + rank))
+        net(x).pow(2).sum().backward()
+        red.allreduce_all()
+        for p, g0, g1 in zip(net.parameters(), *grads):
+            if p.requires_grad:
+                assert torch.allclose(p.grad, (g0 + g1) / 2, atol=1e-6), "allreduce_all mismatch"
+        # a rank-dependent set of parameters with gradients must not reorder the collectives: rank 1 skips the last layer's use
+        red.overlap = True
+        red.reset()
+        y = net[:2](x) if rank == 1 else net[:3](x)
+        y.pow(2).sum().backward()
+        red.finish()
         dist.destroy_process_group()
         print("ok", rank)
     """))

@@ -34,6 +34,7 @@ class GradBucketReducer:
             self._close(cur)
         self._pending = [0] * len(self.buckets)
         self._handles = []
+        self.overlap = True   # False: hooks do nothing, the caller runs allreduce_all() after backward (CUDA-graphed backward)
         self._bucket_of = {}
         for bi, (_, ps) in enumerate(self.buckets):
             for p in ps:
@@ -82,7 +83,28 @@ class GradBucketReducer:
             h = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
             self._handles.append((h, flat))
 
+    def zero_buckets(self):
+        """Zero the flat gradient buffers (capturable: plain memsets)."""
+        for flat, _ in self.buckets:
+            flat.zero_()
+
+    def allreduce_all(self):
+        """Average every bucket over the ranks, in bucket order, without the autograd hooks: for a backward pass that was
+        replayed from a CUDA graph (collectives stay outside the graph; the gradients already sit in the flat buffers)."""
+        if self.world <= 1:
+            return
+        self._handles = []
+        for bi in range(len(self.buckets)):
+            self._launch(bi)
+        for h, flat in self._handles:
+            h.wait()
+            if flat is not None:
+                flat.div_(self.world)
+        self._handles = []
+
     def _hook(self, p):
+        if not self.overlap:
+            return
         bi = self._bucket_of[p]
         if p.grad is None or p.grad.data_ptr() < self.buckets[bi][0].data_ptr() or \
                 p.grad.data_ptr() >= self.buckets[bi][0].data_ptr() + self.buckets[bi][0].numel() * p.element_size():
