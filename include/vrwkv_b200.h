@@ -174,13 +174,17 @@ int vrwkv_gemm_bf16_tn(int M, int N, int K, const uint16_t* A, const uint16_t* B
  * products of model.py:175-194,225-227,325:   C[g] = epilogue(op(A[g]) . op(B[g])), g < ngroups problems of one shape in
  * one launch.  layout bit 0: A is [K,M] (else [M,K]); bit 1: B is [K,N] (else [N,K], the nn.Linear weight layout).
  * epilogue 0 none, 1 relu(.)^2, 2 + R[g], 4 (.) * 2 sqrt(R[g]) (backward of relu^2 from the saved activation),
- * 5 + bias[g][n], 6 tanh-GELU(. + bias), 7 . + bias + R[g][row % r_rows] (the SigLIP tower's Linear layers).
+ * 5 + bias[g][n], 6 tanh-GELU(. + bias), 7 . + bias + R[g][row % r_rows] (the SigLIP tower's Linear layers),
+ * 8 act[g](.) with act 0 none / 1 tanh / 2 sigmoid, 9 (.) * act[g]'(R[g]) from the saved output (the LoRA branches).
  * ksplit > 1 slices the contraction (weight gradients over the 16384 token rows): slices meet in an internal fp32
  * workspace and the last one writes the bf16 result; c_transposed[g] != 0 stores C[g] as [N,M].
- * K % (64 ksplit) == 0, N % 128 == 0, M % 8 == 0 for layout bit 0. */
+ * K % (64 ksplit) == 0, N % 128 == 0, M % 8 == 0 for layout bit 0.
+ * dims (optional, 3 ints per group: Mg, Ng, Kg <= M, N, K, multiples of 8): the group's tensors are exactly that
+ * large (row strides Mg/Ng/Kg); the launch tiles (M, N, K) and the loads zero-fill / the stores clip beyond them, so
+ * LoRA branches of different rank share a launch unpadded. */
 int vrwkv_gemm2_bf16_grouped(int M, int N, int K, int ngroups, const uint16_t* const* A, const uint16_t* const* B,
                              uint16_t* const* C, const uint16_t* const* R, const int* c_transposed, int layout,
-                             int epilogue, int ksplit, const uint16_t* const* bias, int r_rows, void* stream);
+                             int epilogue, int ksplit, const uint16_t* const* bias, int r_rows, const int* act, const int* dims, void* stream);
 int vrwkv_gemm2_bf16(int M, int N, int K, const uint16_t* A, const uint16_t* B, uint16_t* C, int layout, int epilogue,
                      const uint16_t* R, int ksplit, void* stream);
 

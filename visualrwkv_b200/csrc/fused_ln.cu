@@ -217,13 +217,16 @@ __global__ void __launch_bounds__(MAXT) ln_mix_bwd_kernel(const LnMixBwdArgs a) 
         for (int i = 0; i < 2; i++) {
 #pragma unroll
             for (int e = 0; e < LN_VW; e++) {
+                // an invalid row (the empty pending slot of the first iteration, the clamped row past the end) contributes
+                // exact zeros: its x-hat may be anything, and 0 * inf/NaN is not 0
                 const float dh = R[i]->valid ? R[i]->dh.v[e] : 0.f;
+                const float xh = R[i]->valid ? R[i]->xh.v[e] : 0.f;
                 dxh[i].v[e] = dh * g.v[e];
                 if (do_ln) {
                     s[2 * i] += dxh[i].v[e];
-                    s[2 * i + 1] += dxh[i].v[e] * R[i]->xh.v[e];
+                    s[2 * i + 1] += dxh[i].v[e] * xh;
                     if (MODE != 1) {
-                        dgam.v[e] += dh * R[i]->xh.v[e];
+                        dgam.v[e] += dh * xh;
                         dbet.v[e] += dh;
                     }
                 }
@@ -295,6 +298,10 @@ __global__ void __launch_bounds__(MAXT) ln_mix_bwd_kernel(const LnMixBwdArgs a) 
         Row pend;
         pend.valid = false;
         pend.row = row0;
+        pend.xh = zerov();
+        pend.dh = zerov();
+        pend.res = zerov();
+        pend.rstd = 0.f;
         FV Dp = zerov();  // P - Q of the pending row
         const int niter = (row1 - row0 + 2) / 2;  // pairs, plus a final pass for the halo row when the run length is even
         for (int it = 0; it < niter; it++) {

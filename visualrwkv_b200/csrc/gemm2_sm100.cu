@@ -39,7 +39,9 @@ namespace vrwkv {
 constexpr int G2_BM = 128;     // rows per CTA (256 per pair)
 constexpr int G2_BK = 64;
 enum { G2_EPI_NONE = 0, G2_EPI_RELU_SQ = 1, G2_EPI_ADD = 2, G2_EPI_ATOMIC_F32 = 3, G2_EPI_RELUSQ_BWD = 4,
-       G2_EPI_BIAS = 5, G2_EPI_BIAS_GELU = 6, G2_EPI_BIAS_ADD = 7 };   // the SigLIP tower's Linear layers (bias; tanh-GELU; + residual)
+       G2_EPI_BIAS = 5, G2_EPI_BIAS_GELU = 6, G2_EPI_BIAS_ADD = 7,    // the SigLIP tower's Linear layers (bias; tanh-GELU; + residual)
+       G2_EPI_ACT = 8, G2_EPI_ACT_BWD = 9 };   // per-group activation (none / tanh / sigmoid) and its backward from the saved output:
+                                               // the LoRA branches of RWKV_Tmix_x070 (model.py:176,181-184)
 
 constexpr int G2_MAXG = 4;   // problems of identical shape in one launch (r/k/v projections, the four C x C weight gradients, ...)
 struct Gemm2Args {
@@ -50,6 +52,8 @@ struct Gemm2Args {
     const uint16_t* R[G2_MAXG];  // residual (EPI_ADD)
     int ct[G2_MAXG];             // 1: store this group's result transposed (C[g] is [N,M]); EPI_NONE only
     const uint16_t* bias[G2_MAXG];  // [N] (EPI_BIAS*)
+    int act[G2_MAXG];            // EPI_ACT / EPI_ACT_BWD: 0 none, 1 tanh, 2 sigmoid
+    int mv[G2_MAXG], nv[G2_MAXG];   // this group's real result extents (<= M, N): its C / R have nv columns; TMA clips the rest
     int r_rows;                  // rows of R (EPI_BIAS_ADD: R row = row % r_rows — a position table shared by all images); 0 = M
     int dbg_mode;                // development (VRWKV_GEMM2_DBG): 1 = no TMA traffic after the ring is primed (results wrong: tensor-core
                                  // ceiling), 2 = no MMAs (load ceiling)
@@ -219,6 +223,8 @@ gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
         // ===================== epilogue warps (2..9) of both CTAs =====================
         const int q = warp & 3, half = (warp - 2) >> 2;   // TMEM lane quadrant; column half
         int lt = 0;
+        int chunk_i = 0;   // staging buffers alternate across tiles too: with BN = 128 a tile is ONE chunk per warp, and the bulk store of
+                           // the previous tile may still be reading the other buffer (tma_store_wait_read<1> leaves one in flight)
         for (int wk = pair; wk < nwork; wk += npairs, lt++) {
             const int gt = wk / p.ksplit, g = gt / ntiles, tile = gt - g * ntiles;
             const int acc = lt % NACC;
@@ -233,7 +239,6 @@ gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
             // to 32 different rows each cost one L2 transaction per lane and held the epilogue at ~12 k cycles per tile — twice
             // the tensor-core time of a K = 768 tile.  The atomic (split-K) and transposed epilogues keep register stores.
             const bool via_tma = EPI != G2_EPI_ATOMIC_F32 && !(EPI == G2_EPI_NONE && p.ct[g]);
-            int chunk_i = 0;
 #pragma unroll 1
             for (int c64 = half * (BN / 2); c64 < (half + 1) * (BN / 2); c64 += 64, chunk_i++) {
                 uint8_t* const stile = &sm.stg[warp - 2][chunk_i & 1][0];
@@ -248,6 +253,8 @@ gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
                 tmem_ld32(tmem_c + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN + c), r);
                 if (row < p.M || via_tma) {
                     const size_t off = (size_t)row * p.N + n0 + c;
+                    const int nvg = p.nv[g];
+                    const size_t offr = (size_t)row * nvg + n0 + c;   // residuals have the group's real width
                     if (EPI == G2_EPI_ATOMIC_F32) {
 #pragma unroll
                         for (int i = 0; i < 8; i++)
@@ -258,18 +265,19 @@ gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
                         uint4 out[4], res[4];
                         uint32_t* o = reinterpret_cast<uint32_t*>(out);
                         uint4 bia[4];
-                        const bool inb = row < p.M;
-                        if (EPI == G2_EPI_ADD || EPI == G2_EPI_RELUSQ_BWD) {
+                        const bool inb = row < p.mv[g];
+                        if (EPI == G2_EPI_ADD || EPI == G2_EPI_RELUSQ_BWD || EPI == G2_EPI_ACT_BWD) {
 #pragma unroll
-                            for (int i = 0; i < 4; i++) res[i] = inb ? *reinterpret_cast<const uint4*>(Rg + off + 8 * i) : make_uint4(0u, 0u, 0u, 0u);
+                            for (int i = 0; i < 4; i++)
+                                res[i] = (inb && n0 + c + 8 * i < nvg) ? *reinterpret_cast<const uint4*>(Rg + offr + 8 * i) : make_uint4(0u, 0u, 0u, 0u);
                         }
                         if (EPI == G2_EPI_BIAS || EPI == G2_EPI_BIAS_GELU || EPI == G2_EPI_BIAS_ADD) {
 #pragma unroll
-                            for (int i = 0; i < 4; i++) bia[i] = __ldg(reinterpret_cast<const uint4*>(p.bias[g] + n0 + c + 8 * i));
+                            for (int i = 0; i < 4; i++) bia[i] = (n0 + c + 8 * i < nvg) ? __ldg(reinterpret_cast<const uint4*>(p.bias[g] + n0 + c + 8 * i)) : make_uint4(0u, 0u, 0u, 0u);
                             if (EPI == G2_EPI_BIAS_ADD) {
-                                const size_t roff = (size_t)(p.r_rows ? row % p.r_rows : row) * p.N + n0 + c;
+                                const size_t roff = (size_t)(p.r_rows ? row % p.r_rows : row) * nvg + n0 + c;
 #pragma unroll
-                                for (int i = 0; i < 4; i++) res[i] = inb ? *reinterpret_cast<const uint4*>(Rg + roff + 8 * i) : make_uint4(0u, 0u, 0u, 0u);
+                                for (int i = 0; i < 4; i++) res[i] = (inb && n0 + c + 8 * i < nvg) ? *reinterpret_cast<const uint4*>(Rg + roff + 8 * i) : make_uint4(0u, 0u, 0u, 0u);
                             }
                         }
                         const uint32_t* bb = reinterpret_cast<const uint32_t*>(bia);
@@ -297,6 +305,21 @@ gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
                                     x0 += bf16lo_to_f32(rr[i]);
                                     x1 += bf16hi_to_f32(rr[i]);
                                 }
+                            } else if (EPI == G2_EPI_ACT) {
+                                // eager graph: the matmul output is rounded to bf16, then tanh / sigmoid in fp32
+                                x0 = __bfloat162float(__float2bfloat16_rn(x0));
+                                x1 = __bfloat162float(__float2bfloat16_rn(x1));
+                                const int ac = p.act[g];
+                                if (ac == 1) { x0 = tanhf(x0); x1 = tanhf(x1); }
+                                else if (ac == 2) { x0 = 1.f / (1.f + __expf(-x0)); x1 = 1.f / (1.f + __expf(-x1)); }
+                            } else if (EPI == G2_EPI_ACT_BWD) {
+                                // d/dx tanh = 1 - h^2, d/dx sigmoid = h (1 - h), from the saved output h
+                                x0 = __bfloat162float(__float2bfloat16_rn(x0));
+                                x1 = __bfloat162float(__float2bfloat16_rn(x1));
+                                const float h0 = bf16lo_to_f32(rr[i]), h1 = bf16hi_to_f32(rr[i]);
+                                const int ac = p.act[g];
+                                if (ac == 1) { x0 *= (1.f - h0 * h0); x1 *= (1.f - h1 * h1); }
+                                else if (ac == 2) { x0 *= (1.f - h0) * h0; x1 *= (1.f - h1) * h1; }
                             } else if (EPI == G2_EPI_RELUSQ_BWD) {
                                 // eager graph: dact -> bf16, then d/dx relu(x)^2 = 2 relu(x) = 2 sqrt(act)
                                 x0 = __bfloat162float(__float2bfloat16_rn(x0)) * 2.f * sqrtf(bf16lo_to_f32(rr[i]));
@@ -309,7 +332,8 @@ gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
                             const uint16_t* o16 = reinterpret_cast<const uint16_t*>(out);
                             if (inb) {
 #pragma unroll
-                                for (int i = 0; i < 32; i++) Cg[(size_t)(n0 + c + i) * p.M + row] = o16[i];
+                                for (int i = 0; i < 32; i++)
+                                    if (n0 + c + i < nvg) Cg[(size_t)(n0 + c + i) * p.mv[g] + row] = o16[i];
                             }
                         } else {
                             // staging tile row = lane, 128 bytes (64 columns), 16-byte chunks XOR-swizzled by (row & 7)
@@ -343,13 +367,14 @@ gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
                     __threadfence();
                     if (lane == 0) *ticket = 0;
                     if (row < p.M) {
+                        const int mvg = p.mv[g], nvg = p.nv[g];
 #pragma unroll 1
                         for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 8) {
                             float4* src = reinterpret_cast<float4*>(Cfg + (size_t)row * p.N + n0 + c);
                             const float4 x = __ldcg(src), y = __ldcg(src + 1);
                             uint4 o;
                             o.x = pack_bf16x2(x.x, x.y); o.y = pack_bf16x2(x.z, x.w); o.z = pack_bf16x2(y.x, y.y); o.w = pack_bf16x2(y.z, y.w);
-                            *reinterpret_cast<uint4*>(Cg + (size_t)row * p.N + n0 + c) = o;
+                            if (row < mvg && n0 + c < nvg) *reinterpret_cast<uint4*>(Cg + (size_t)row * nvg + n0 + c) = o;
                             src[0] = make_float4(0.f, 0.f, 0.f, 0.f);
                             src[1] = make_float4(0.f, 0.f, 0.f, 0.f);
                         }
@@ -427,7 +452,7 @@ static int g2_workspace(size_t cf_elems, size_t n_tickets, cudaStream_t st, G2Wo
 // writes the bf16 result (no element-wise epilogue in that mode).
 extern "C" int vrwkv_gemm2_bf16_grouped(int M, int N, int K, int ngroups, const uint16_t* const* A, const uint16_t* const* B,
                                         uint16_t* const* C, const uint16_t* const* R, const int* c_transposed, int layout, int epilogue,
-                                        int ksplit, const uint16_t* const* bias, int r_rows, void* stream) {
+                                        int ksplit, const uint16_t* const* bias, int r_rows, const int* act, const int* dims, void* stream) {
     if (M <= 0 || N <= 0 || K <= 0) return vrwkv_fail(VRWKV_EINVAL, "gemm2: bad shape (%d,%d,%d)", M, N, K);
     if (ngroups < 1 || ngroups > G2_MAXG) return vrwkv_fail(VRWKV_EINVAL, "gemm2: 1..%d groups (got %d)", G2_MAXG, ngroups);
     if (ksplit < 1) ksplit = 1;
@@ -436,9 +461,9 @@ extern "C" int vrwkv_gemm2_bf16_grouped(int M, int N, int K, int ngroups, const 
     const int a_mn = layout & 1, b_mn = (layout >> 1) & 1;
     if (a_mn && (M % 8)) return vrwkv_fail(VRWKV_EUNSUP, "gemm2: M=%d must be a multiple of 8 when A is stored [K,M]", M);
     if (ksplit > 1 && epilogue != G2_EPI_NONE) return vrwkv_fail(VRWKV_EINVAL, "gemm2: no element-wise epilogue with ksplit > 1");
-    if (epilogue < 0 || epilogue > G2_EPI_BIAS_ADD || epilogue == G2_EPI_ATOMIC_F32) return vrwkv_fail(VRWKV_EINVAL, "gemm2: unknown epilogue %d", epilogue);
-    const bool need_r = epilogue == G2_EPI_ADD || epilogue == G2_EPI_RELUSQ_BWD || epilogue == G2_EPI_BIAS_ADD;
-    const bool need_b = epilogue >= G2_EPI_BIAS;
+    if (epilogue < 0 || epilogue > G2_EPI_ACT_BWD || epilogue == G2_EPI_ATOMIC_F32) return vrwkv_fail(VRWKV_EINVAL, "gemm2: unknown epilogue %d", epilogue);
+    const bool need_r = epilogue == G2_EPI_ADD || epilogue == G2_EPI_RELUSQ_BWD || epilogue == G2_EPI_BIAS_ADD || epilogue == G2_EPI_ACT_BWD;
+    const bool need_b = epilogue >= G2_EPI_BIAS && epilogue <= G2_EPI_BIAS_ADD;
     if (need_b && (layout != 0 || !bias)) return vrwkv_fail(VRWKV_EINVAL, "gemm2: bias epilogues need the [M,K] x [N,K] layout and a bias per group");
     const int BN = (N % 256 == 0) ? 256 : 128;
     cudaStream_t st = (cudaStream_t)stream;
@@ -454,21 +479,28 @@ extern "C" int vrwkv_gemm2_bf16_grouped(int M, int N, int K, int ngroups, const 
         if ((((uintptr_t)A[g]) | ((uintptr_t)B[g]) | ((uintptr_t)C[g]) | (R ? (uintptr_t)R[g] : 0)) & 15)
             return vrwkv_fail(VRWKV_EINVAL, "gemm2: pointers must be 16-byte aligned");
         int rc;
-        // K-major operand: matrix [rows = M|N][cols = K], box [128 | BN/2 rows][64 cols];  MN-major: matrix [rows = K][cols = M|N], box [64][64]
-        if (a_mn) rc = vrwkv_encode_2d(&maps.a[g], A[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)K, (uint64_t)M * 2, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
-        else rc = vrwkv_encode_2d(&maps.a[g], A[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, G2_BK, G2_BM, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (rc) return rc;
-        if (b_mn) rc = vrwkv_encode_2d(&maps.b[g], B[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)N, (uint64_t)K, (uint64_t)N * 2, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
-        else rc = vrwkv_encode_2d(&maps.b[g], B[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, G2_BK, BN / 2, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (rc) return rc;
+        // The group's real extents: its tensors are exactly [Mg | Ng | Kg] wide; the launch tiles the common (M, N, K) and TMA
+        // zero-fills loads / clips stores beyond them (LoRA ranks 32..128 share one launch this way, unpadded).
+        const uint64_t Mg = dims ? dims[3 * g] : M, Ng = dims ? dims[3 * g + 1] : N, Kg = dims ? dims[3 * g + 2] : K;
+        if (Mg < 1 || Ng < 1 || Kg < 1 || Mg > (uint64_t)M || Ng > (uint64_t)N || Kg > (uint64_t)K || (Ng % 8) || (Kg % 8) || (a_mn && (Mg % 8)))
+            return vrwkv_fail(VRWKV_EINVAL, "gemm2: group %d extents (%d,%d,%d) must be multiples of 8 within (%d,%d,%d)", g, (int)Mg, (int)Ng, (int)Kg, M, N, K);
         const bool transposed = c_transposed && c_transposed[g];
-        if ((rc = vrwkv_encode_2d(&maps.c[g], C[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, transposed ? (uint64_t)M : (uint64_t)N,
-                                  transposed ? (uint64_t)N : (uint64_t)M, (transposed ? (uint64_t)M : (uint64_t)N) * 2, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B)))
+        a.mv[g] = (int)Mg; a.nv[g] = (int)Ng;
+        // K-major operand: matrix [rows = M|N][cols = K], box [128 | BN/2 rows][64 cols];  MN-major: matrix [rows = K][cols = M|N], box [64][64]
+        if (a_mn) rc = vrwkv_encode_2d(&maps.a[g], A[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mg, Kg, Mg * 2, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+        else rc = vrwkv_encode_2d(&maps.a[g], A[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Kg, Mg, Kg * 2, G2_BK, G2_BM, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        if (b_mn) rc = vrwkv_encode_2d(&maps.b[g], B[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Ng, Kg, Ng * 2, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+        else rc = vrwkv_encode_2d(&maps.b[g], B[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Kg, Ng, Kg * 2, G2_BK, BN / 2, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        if ((rc = vrwkv_encode_2d(&maps.c[g], C[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, transposed ? Mg : Ng,
+                                  transposed ? Ng : Mg, (transposed ? Mg : Ng) * 2, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B)))
             return rc;
         a.C[g] = C[g];
         a.R[g] = R ? R[g] : nullptr;
         a.ct[g] = (c_transposed && c_transposed[g]) ? 1 : 0;
         a.bias[g] = need_b ? bias[g] : nullptr;
+        a.act[g] = act ? act[g] : 0;
         if (a.ct[g] && (epilogue != G2_EPI_NONE || ksplit > 1)) return vrwkv_fail(VRWKV_EINVAL, "gemm2: transposed store only with the plain epilogue");
     }
     for (int g = ngroups; g < G2_MAXG; g++) { maps.a[g] = maps.a[0]; maps.b[g] = maps.b[0]; maps.c[g] = maps.c[0]; }
@@ -489,6 +521,7 @@ extern "C" int vrwkv_gemm2_bf16_grouped(int M, int N, int K, int ngroups, const 
     G2_CASE(256, G2_EPI_RELUSQ_BWD, 0, 1)
     G2_LAYOUTS(128, G2_EPI_NONE) G2_LAYOUTS(128, G2_EPI_ADD) G2_LAYOUTS(128, G2_EPI_ATOMIC_F32) G2_CASE(128, G2_EPI_RELU_SQ, 0, 0)
     G2_CASE(128, G2_EPI_RELUSQ_BWD, 0, 1)
+    G2_CASE(256, G2_EPI_ACT, 0, 1) G2_CASE(128, G2_EPI_ACT, 0, 1) G2_CASE(256, G2_EPI_ACT_BWD, 0, 0) G2_CASE(128, G2_EPI_ACT_BWD, 0, 0)
     G2_CASE(256, G2_EPI_BIAS, 0, 0) G2_CASE(256, G2_EPI_BIAS_GELU, 0, 0) G2_CASE(256, G2_EPI_BIAS_ADD, 0, 0)
     G2_CASE(128, G2_EPI_BIAS, 0, 0) G2_CASE(128, G2_EPI_BIAS_GELU, 0, 0) G2_CASE(128, G2_EPI_BIAS_ADD, 0, 0)
 #undef G2_LAYOUTS
@@ -498,5 +531,5 @@ extern "C" int vrwkv_gemm2_bf16_grouped(int M, int N, int K, int ngroups, const 
 
 extern "C" int vrwkv_gemm2_bf16(int M, int N, int K, const uint16_t* A, const uint16_t* B, uint16_t* C, int layout, int epilogue,
                                 const uint16_t* R, int ksplit, void* stream) {
-    return vrwkv_gemm2_bf16_grouped(M, N, K, 1, &A, &B, &C, &R, nullptr, layout, epilogue, ksplit, nullptr, 0, stream);
+    return vrwkv_gemm2_bf16_grouped(M, N, K, 1, &A, &B, &C, &R, nullptr, layout, epilogue, ksplit, nullptr, 0, nullptr, nullptr, stream);
 }

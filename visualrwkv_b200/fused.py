@@ -15,6 +15,7 @@ import ctypes
 import os
 
 import torch
+import torch.nn.functional as F
 
 from . import _lib
 from . import wkv7 as _wkv7
@@ -236,19 +237,31 @@ class TmixBlockFn(torch.autograd.Function):
             r = xr @ Wr.t()
             k = xk @ Wk.t()
             v = xv @ Wv.t()
-        hw = torch.tanh(xw @ w1)
-        ww = hw @ w2
-        ha = xa @ a1
-        aa = ha @ a2
-        hg = torch.sigmoid(xg @ g1)
-        g = hg @ g2
         has_vres = layer_id != 0
-        if has_vres:
-            hv = xv @ v1
-            vv = hv @ v2
-            vf2 = v_first.reshape(rows, C).contiguous()
+        vf2 = v_first.reshape(rows, C).contiguous() if has_vres else None
+        lora_own = own and _lora_ok(w1, a1, g1, v1 if has_vres else None)
+        if lora_own:
+            # the LoRA branches (model.py:176,181-184) as two grouped launches (ranks differ per branch; the launch tiles the
+            # widest and TMA zero-fills the rest): down-projections with their activation in the epilogue, then up-projections
+            downs = [(xw, w1, ACT_TANH), (xa, a1, ACT_NONE), (xg, g1, ACT_SIGMOID)] + ([(xv, v1, ACT_NONE)] if has_vres else [])
+            ups = [w2, a2, g2] + ([v2] if has_vres else [])
+            hs = gemm2_grouped([xx for xx, _, _ in downs], [wd for _, wd, _ in downs], G2_NN, EPI_ACT, acts=[ac for _, _, ac in downs])
+            outs = gemm2_grouped(hs, ups, G2_NN)
+            hw, ha, hg = hs[:3]
+            ww, aa, g = outs[:3]
+            hv, vv = (hs[3], outs[3]) if has_vres else (None, None)
         else:
-            hv = vv = vf2 = None
+            hw = torch.tanh(xw @ w1)
+            ww = hw @ w2
+            ha = xa @ a1
+            aa = ha @ a2
+            hg = torch.sigmoid(xg @ g1)
+            g = hg @ g2
+            if has_vres:
+                hv = xv @ v1
+                vv = hv @ v2
+            else:
+                hv = vv = None
         w, k2, v2_, nkk, kka = tmix_mid_forward(k, v, vf2, ww, aa, vv, w0.reshape(C), a0.reshape(C),
                                                 v0.reshape(C) if has_vres else None, k_k.reshape(C), k_a.reshape(C))
         H = n_head
@@ -263,6 +276,7 @@ class TmixBlockFn(torch.autograd.Function):
                               w, k2, v2_, nkk, kka, y, s, sa, z, w0, w1, w2, a0, a1, a2, v0, v1, v2, g1, g2, k_k, k_a, r_k,
                               Wr, Wk, Wv, Wo, lnx_w, lnx_b)
         ctx.meta = (B, T, C, H, layer_id, ln_eps, gn_eps, with_ln)
+        ctx.lora_own = lora_own
         v_out = v.view(B, T, C)  # layer 0: this is v_first; later layers: ignored by the caller
         if has_vres:
             ctx.mark_non_differentiable(v_out)
@@ -289,33 +303,54 @@ class TmixBlockFn(torch.autograd.Function):
         if not has_vres and dvfirst_out is not None:
             dv.add_(dvfirst_out.reshape(rows, C))
         # LoRA branches
-        dhg = dg @ g2.t()
-        dg2 = hg.t() @ dg
-        dpg = torch.ops.aten.sigmoid_backward(dhg, hg)
-        dxg = dpg @ g1.t()
-        dg1 = xg.t() @ dpg
-        dhw = dww @ w2.t()
-        dw2 = hw.t() @ dww
-        dpw = torch.ops.aten.tanh_backward(dhw, hw)
-        dxw = dpw @ w1.t()
-        dw1 = xw.t() @ dpw
-        dha = daa @ a2.t()
-        da2 = ha.t() @ daa
-        dxa = dha @ a1.t()
-        da1 = xa.t() @ dha
-        # main projections
-        if has_vres:
-            dhv = dvv @ v2.t()
-            dv2p = hv.t() @ dvv
-            dv1 = xv.t() @ dhv
+        if ctx.lora_own:
+            douts = [dww, daa, dg] + ([dvv] if has_vres else [])
+            hs = [hw, ha, hg] + ([hv] if has_vres else [])
+            xs = [xw, xa, xg] + ([xv] if has_vres else [])
+            downs = [w1, a1, g1] + ([v1] if has_vres else [])
+            ups = [w2, a2, g2] + ([v2] if has_vres else [])
+            acts = [ACT_TANH, ACT_NONE, ACT_SIGMOID] + ([ACT_NONE] if has_vres else [])
+            ng, Rp = len(hs), max(h.shape[1] for h in hs)
+            dps = gemm2_grouped(douts, ups, G2_TN, EPI_ACT_BWD, residuals=hs, acts=acts)        # d(pre-activation) [rows, rank]
+            dxl = gemm2_grouped(dps, downs, G2_TN)                                              # [rows, C]
+            dU = gemm2_grouped(hs, douts, G2_TT, ksplit=min(4, _ksplit(ng, Rp, C, rows)))       # h^T dout [rank, C]
+            dD = gemm2_grouped(xs, dps, G2_TT, ksplit=min(4, _ksplit(ng, C, Rp, rows)))         # x^T dpre [C, rank]
+            dw2, da2, dg2 = dU[:3]
+            dw1, da1, dg1 = dD[:3]
+            dxw, dxa, dxg = dxl[:3]
+            if has_vres:
+                dv2p, dv1, dxv_lora = dU[3], dD[3], dxl[3]
+            else:
+                dv2p = dv1 = dxv_lora = None
         else:
-            dv2p = dv1 = None
+            dhg = dg @ g2.t()
+            dg2 = hg.t() @ dg
+            dpg = torch.ops.aten.sigmoid_backward(dhg, hg)
+            dxg = dpg @ g1.t()
+            dg1 = xg.t() @ dpg
+            dhw = dww @ w2.t()
+            dw2 = hw.t() @ dww
+            dpw = torch.ops.aten.tanh_backward(dhw, hw)
+            dxw = dpw @ w1.t()
+            dw1 = xw.t() @ dpw
+            dha = daa @ a2.t()
+            da2 = ha.t() @ daa
+            dxa = dha @ a1.t()
+            da1 = xa.t() @ dha
+            if has_vres:
+                dhv = dvv @ v2.t()
+                dv2p = hv.t() @ dvv
+                dv1 = xv.t() @ dhv
+                dxv_lora = dhv @ v1.t()
+            else:
+                dv2p = dv1 = dxv_lora = None
+        # main projections
         if own:
             # dgrad: dx = dy W (W is [out, in]: contraction over its rows); wgrad: dW = dy^T x over the token rows, the
             # four C x C weight gradients of the block in one split-K launch
             if has_vres:
                 dxr, dxk = gemm2_grouped([dr, dk], [Wr, Wk], G2_NN)
-                dxv = gemm2(dv, Wv, G2_NN, EPI_ADD, dhv @ v1.t())
+                dxv = gemm2(dv, Wv, G2_NN, EPI_ADD, dxv_lora)
             else:
                 dxr, dxk, dxv = gemm2_grouped([dr, dk, dv], [Wr, Wk, Wv], G2_NN)
             dWo, dWr, dWk, dWv = gemm2_grouped([do, dr, dk, dv], [z, xr, xk, xv], G2_TT, ksplit=_ksplit(4, C, C, rows))
@@ -326,7 +361,7 @@ class TmixBlockFn(torch.autograd.Function):
             dxk = dk @ Wk
             dWk = dk.t() @ xk
             dWv = dv.t() @ xv
-            dxv = torch.addmm(dhv @ v1.t(), dv, Wv) if has_vres else dv @ Wv
+            dxv = torch.addmm(dxv_lora, dv, Wv) if has_vres else dv @ Wv
         coefs = [c_r, c_w, c_k, c_v, c_a, c_g]
         dx, dlnw, dlnb, dco = ln_mix_backward(x2, T, stats, ln_w if with_ln else None, ln_b if with_ln else None, coefs,
                                               [dxr, dxw, dxk, dxv, dxa, dxg], dresid=do if with_ln else None)
@@ -474,29 +509,41 @@ def gemm_supported(M, N, K):
 G2_TN, G2_NN, G2_TT = 0, 2, 3     # layout bits: 1 = A stored [K,M], 2 = B stored [K,N]
 
 
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_ADD = 5, 6, 7
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_ADD, EPI_ACT, EPI_ACT_BWD = 5, 6, 7, 8, 9
+ACT_NONE, ACT_TANH, ACT_SIGMOID = 0, 1, 2
 
 
-def gemm2_grouped(As, Bs, layout=G2_TN, epilogue=EPI_NONE, residuals=None, ksplit=1, transposed=None, biases=None, r_rows=0):
-    """[epilogue(op(a) . op(b)) for a, b in zip(As, Bs)] in ONE launch (identical shapes), bf16 in / out, fp32 accumulate.
+def gemm2_grouped(As, Bs, layout=G2_TN, epilogue=EPI_NONE, residuals=None, ksplit=1, transposed=None, biases=None, r_rows=0, acts=None):
+    """[epilogue(op(a) . op(b)) for a, b in zip(As, Bs)] in ONE launch, bf16 in / out, fp32 accumulate.
       G2_TN: a [M,K], b [N,K]  -> a @ b.T      (forward y = x W^T)
       G2_NN: a [M,K], b [K,N]  -> a @ b        (dgrad  dx = dy W)
-      G2_TT: a [K,M], b [K,N]  -> a.T @ b      (wgrad  dW = dy^T x; ksplit > 1 slices the long contraction)"""
+      G2_TT: a [K,M], b [K,N]  -> a.T @ b      (wgrad  dW = dy^T x; ksplit > 1 slices the long contraction)
+    Groups may differ in shape (the LoRA ranks): the launch tiles the largest, rounded up to the tile, and each group's
+    tensors keep their own exact size."""
     L = _lib.lib()
-    a, b = As[0], Bs[0]
     _bf16c(*As, *Bs, *(residuals or []), *(biases or []))
     a_mn, b_mn = layout & 1, (layout >> 1) & 1
-    M, K = (a.shape[1], a.shape[0]) if a_mn else a.shape
-    N = b.shape[1] if b_mn else b.shape[0]
-    assert (b.shape[0] if b_mn else b.shape[1]) == K and all(x.shape == a.shape for x in As) and all(x.shape == b.shape for x in Bs)
+    dims = []
+    for a, b in zip(As, Bs):
+        Mg, Kg = (a.shape[1], a.shape[0]) if a_mn else a.shape
+        Ng, Kb = (b.shape[1], b.shape[0]) if b_mn else b.shape
+        assert Kb == Kg, (a.shape, b.shape)
+        dims.append((Mg, Ng, Kg))
+    M = max(d[0] for d in dims)
+    N = -(-max(d[1] for d in dims) // 128) * 128
+    K = -(-max(d[2] for d in dims) // (64 * ksplit)) * (64 * ksplit)
+    ragged = any(d != (M, N, K) for d in dims)
     tr = list(transposed) if transposed else [0] * len(As)
-    Cs = [torch.empty((N, M) if t else (M, N), dtype=torch.bfloat16, device=a.device) for t in tr]   # transposed[g]: C[g] = (a.b)^T
+    dev = As[0].device
+    Cs = [torch.empty((Ng, Mg) if t else (Mg, Ng), dtype=torch.bfloat16, device=dev) for t, (Mg, Ng, _) in zip(tr, dims)]   # transposed[g]: (a.b)^T
+    flat = [v for d in dims for v in d]
     _chk(L.vrwkv_gemm2_bf16_grouped(_c_int(M), _c_int(N), _c_int(K), _c_int(len(As)), _parr(As), _parr(Bs), _parr(Cs),
                                     _parr(residuals) if residuals else None, (_c_int * len(tr))(*tr), _c_int(layout), _c_int(epilogue),
-                                    _c_int(ksplit), _parr(biases) if biases else None, _c_int(r_rows), _lib.cur_stream()),
+                                    _c_int(ksplit), _parr(biases) if biases else None, _c_int(r_rows),
+                                    (_c_int * len(acts))(*acts) if acts else None, (_c_int * len(flat))(*flat) if ragged else None,
+                                    _lib.cur_stream()),
          "vrwkv_gemm2_bf16_grouped")
     return Cs
-
 
 def gemm2(a, b, layout=G2_TN, epilogue=EPI_NONE, residual=None, ksplit=1, bias=None, r_rows=0):
     return gemm2_grouped([a], [b], layout, epilogue, [residual] if residual is not None else None, ksplit,
@@ -508,7 +555,13 @@ HEAD_OWN_GEMM = os.environ.get("VRWKV_HEAD_GEMM", "own") == "own"   # "cublas": 
 
 
 def gemm2_supported(M, N, K, ksplit=1):
-    return K % (64 * ksplit) == 0 and N % 128 == 0 and M % 8 == 0 and M > 0
+    """Extents the CTA-pair GEMM takes: multiples of 8 (16-byte TMA row strides); tiles past the edge are zero-filled / clipped."""
+    return K % 8 == 0 and N % 8 == 0 and M % 8 == 0 and M > 0
+
+
+def _lora_ok(*downs):
+    """The LoRA ranks the grouped launches take: multiples of 8 (TMA row strides of 16 bytes)."""
+    return all(d.shape[1] % 8 == 0 for d in downs if d is not None)
 
 
 def _ksplit(groups, M, N, K):
