@@ -114,6 +114,7 @@ int vrwkv_wkv7_set_variant(int fwd_variant, int bwd_variant);
  * nmix in {0,1,6}; gamma == beta == NULL: input already normalised (mix only); out[m] = h + (shift(h) - h) coef[m].
  * coef / out / dout are HOST arrays of nmix device pointers.  stats: f32 [rows,2] (mean, rstd). */
 int vrwkv_ln_mix_blocks(int rows);
+int vrwkv_ln_mix_blocks2(int rows, int C);   /* partial rows vrwkv_ln_mix_backward writes for this shape (use this one) */
 int vrwkv_ln_mix_forward(int rows, int T, int C, int nmix, float eps, const uint16_t* x, const uint16_t* gamma,
                          const uint16_t* beta, const uint16_t* const* coef, uint16_t* const* out, uint16_t* h_out,
                          float* stats, void* stream);

@@ -72,7 +72,7 @@ def ln_mix_backward(x2d, T, stats, gamma, beta, coefs, douts, dh=None, dresid=No
     L = _lib.lib()
     rows, C = x2d.shape
     _bf16c(x2d, gamma, beta, dh, dresid, *coefs, *douts)
-    nb = L.vrwkv_ln_mix_blocks(_c_int(rows))
+    nb = L.vrwkv_ln_mix_blocks2(_c_int(rows), _c_int(C))
     partial = torch.empty(nb, 2 + len(coefs), C, dtype=torch.float32, device=x2d.device)
     dx = torch.empty_like(x2d)
     rc = L.vrwkv_ln_mix_backward(_c_int(rows), _c_int(T), _c_int(C), _c_int(len(coefs)), _p(x2d), _p(stats), _p(gamma), _p(beta),
