@@ -157,6 +157,8 @@ def main():
                          "strict parity tests), step (step-by-step fp32 kernels), tf32 (round-1 kernels, outside the tolerance)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step as one CUDA graph (visualrwkv_b200.graph.GraphedTrainStep); auto = on")
+    ap.add_argument("--optimizer", default="own", choices=["own", "torch"],
+                    help="own: visualrwkv_b200.optim.FusedAdamW (one multi-tensor kernel); torch: stock fused AdamW on fp32 copies")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-kernel", action="store_true")
     ap.add_argument("--grad-cp", type=int, default=0)
@@ -211,13 +213,19 @@ def main():
     model.freeze_emb()  # v7.00/train.py:196: emb is always frozen
     trainable = [p for p in model.parameters() if p.requires_grad]
     reducer = GradBucketReducer(trainable) if world > 1 else None
-    # bf16 params + fp32 master/Adam state (what DeepSpeed bf16 keeps), fused AdamW
-    master = [p.detach().float().clone() for p in trainable]
-    for mp in master:
-        mp.grad = torch.zeros_like(mp)
+    # bf16 params + fp32 master/Adam state (what DeepSpeed bf16 keeps): one multi-tensor AdamW kernel (csrc/optim.cu);
+    # --optimizer torch: stock PyTorch (bf16 -> fp32 gradient copy, fused AdamW on fp32 copies, copy back)
     use_graph = a.graph != "off"
-    opt = torch.optim.AdamW(master, lr=torch.tensor(1e-5, device=dev) if use_graph else 1e-5, betas=(0.9, 0.99), eps=1e-8,
-                            weight_decay=0.0, fused=True, capturable=use_graph)
+    if a.optimizer == "own":
+        from visualrwkv_b200.optim import FusedAdamW
+        opt = FusedAdamW(trainable, lr=1e-5, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.0)
+        master = None
+    else:
+        master = [p.detach().float().clone() for p in trainable]
+        for mp in master:
+            mp.grad = torch.zeros_like(mp)
+        opt = torch.optim.AdamW(master, lr=torch.tensor(1e-5, device=dev) if use_graph else 1e-5, betas=(0.9, 0.99), eps=1e-8,
+                                weight_decay=0.0, fused=True, capturable=use_graph)
 
     B, T = a.batch, a.ctx
     host = make_batch(B, T, 576, 224, seed=100 + rank, img_dtype=torch.bfloat16)
@@ -227,9 +235,12 @@ def main():
 
     def apply_grads_local():
         with torch.no_grad():
-            torch._foreach_copy_([m.grad for m in master], [p.grad for p in trainable])
-            opt.step()
-            torch._foreach_copy_(trainable, master)
+            if master is None:
+                opt.step()
+            else:
+                torch._foreach_copy_([m.grad for m in master], [p.grad for p in trainable])
+                opt.step()
+                torch._foreach_copy_(trainable, master)
 
     def apply_grads():
         if reducer is not None:
@@ -289,6 +300,8 @@ def main():
             train_step = eager_step
             torch.cuda.synchronize()
     config["launch"] = graph_note
+    config["optimizer"] = "AdamW, fp32 master + moments, " + ("one multi-tensor kernel (csrc/optim.cu)" if a.optimizer == "own"
+                                                                else "torch fused AdamW on fp32 copies")
 
     def e2e_step():
         if train_step is not eager_step:

@@ -209,6 +209,20 @@ int vrwkv_im2col_patches(int N, int Hp, int Wp, int P, const uint16_t* pixels, u
 int vrwkv_sigmul_forward(size_t n, const uint16_t* x, const uint16_t* g, uint16_t* h, void* stream);
 int vrwkv_sigmul_backward(size_t n, const uint16_t* x, const uint16_t* g, const uint16_t* dh, uint16_t* dx, uint16_t* dg, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Optimizer step of the training loop: AdamW over bf16 parameters with fp32 master weights and moments (the reference
+ * configures DeepSpeed FusedAdam in adam_w_mode over bf16 weights, v7.00/src/model.py:376-410).  One multi-tensor pass:
+ * reads the bf16 gradient and the fp32 state, writes the state and the bf16 parameter (28 bytes per parameter).
+ * tensors: device array of 32-byte records {bf16* param, const bf16* grad, int64 state_off, int64 numel};
+ * chunks: device array of int2 {tensor index, chunk index}, chunk = vrwkv_adamw_chunk() elements;
+ * step: device int, incremented before the update (bias correction), so a call is CUDA-graph capturable;
+ * lr_dev: optional device float overriding lr;  grad_scale multiplies the gradient (e.g. 1 / world size).
+ * --------------------------------------------------------------------------------------------- */
+int vrwkv_adamw_chunk(void);
+int vrwkv_adamw_step(int nchunks, const void* tensors, const void* chunks, float* master, float* exp_avg, float* exp_avg_sq,
+                     int* step, const float* lr_dev, float lr, float beta1, float beta2, float eps, float weight_decay,
+                     float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

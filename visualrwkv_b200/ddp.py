@@ -14,6 +14,10 @@ import torch
 import torch.distributed as dist
 
 
+def _al(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
 class GradBucketReducer:
     def __init__(self, params, bucket_bytes: int = 32 << 20, process_group=None):
         self.pg = process_group
@@ -43,12 +47,12 @@ class GradBucketReducer:
         self.reset()
 
     def _close(self, ps):
-        n = sum(p.numel() for p in ps)
+        n = sum(_al(p.numel()) for p in ps)   # every gradient view starts on a 16-byte boundary (vector loads in the optimizer kernel)
         flat = torch.zeros(n, dtype=ps[0].dtype, device=ps[0].device)
         off = 0
         for p in ps:
             p.grad = flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+            off += _al(p.numel())
         self.buckets.append((flat, ps))
 
     def _rebind(self):
@@ -63,7 +67,7 @@ class GradBucketReducer:
                     if p.grad is not None:
                         view.copy_(p.grad)
                     p.grad = view
-                off += p.numel()
+                off += _al(p.numel())
 
     def reset(self):
         """Call once per step before backward: zero the flat gradient buffers (grads are views into them)."""
