@@ -18,6 +18,8 @@ LIB = os.path.join(PKG, "libvrwkv_b200.so")
 SHIM = os.path.join(PKG, "libvrwkv_torch_shim.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+if os.environ.get("VRWKV_PHASE_STAMPS"):   # development builds: per-phase clock stamps in the x6 / x3 WKV7 kernels
+    NVCC_FLAGS.append("-DVRWKV_PHASE_STAMPS")
 CXX = "/usr/bin/g++"
 
 

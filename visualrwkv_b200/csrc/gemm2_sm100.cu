@@ -115,6 +115,12 @@ struct alignas(1024) Gemm2Smem {
     uint32_t tmem_base;
 };
 
+__device__ __forceinline__ float g2_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 template <int BN, int EPI, int A_MN, int B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
@@ -223,6 +229,32 @@ gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
         // ===================== epilogue warps (2..9) of both CTAs =====================
         const int q = warp & 3, half = (warp - 2) >> 2;   // TMEM lane quadrant; column half
         int lt = 0;
+        // Residual operand of the epilogue (ADD / RELUSQ_BWD / BIAS_ADD / ACT_BWD): this warp's 32 x 64 tiles are fetched with
+        // row-contiguous accesses (8 lanes x 16 bytes = one 128-byte line per row, 4 rows per instruction), ONE TILE AHEAD, and
+        // pass through the staging tile to the lane that owns the row.  (One 16-byte load per lane from 32 different rows
+        // made the relu^2-backward GEMM 3.4x slower than its forward twin; loading at the start of the tile's own epilogue
+        // still exposed the round trip: 104 vs 60 us with a plain residual add at N = 3072.)
+        constexpr bool NEED_R = EPI == G2_EPI_ADD || EPI == G2_EPI_RELUSQ_BWD || EPI == G2_EPI_BIAS_ADD || EPI == G2_EPI_ACT_BWD;
+        constexpr int NCH = BN / 128;   // 64-column chunks per warp per tile
+        uint4 rpre[NEED_R ? NCH : 1][8], rnext[NEED_R ? NCH : 1][8];
+        auto load_r = [&](int wk_, uint4 (&dst)[NEED_R ? NCH : 1][8]) {
+            const int gt_ = wk_ / p.ksplit, g_ = gt_ / ntiles, tile_ = gt_ - g_ * ntiles;
+            const int m0_ = (tile_ / ntn) * 2 * G2_BM + (int)rank * G2_BM, n0_ = (tile_ % ntn) * BN;
+            const int mvg = p.mv[g_], nvg = p.nv[g_];
+            const uint16_t* const Rg_ = p.R[g_];
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch++)
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int grow = m0_ + 32 * q + 4 * k + (lane >> 3), gcol = n0_ + half * (BN / 2) + 64 * ch + 8 * (lane & 7);
+                    const int srow = (EPI == G2_EPI_BIAS_ADD && p.r_rows) ? grow % p.r_rows : grow;
+                    dst[ch][k] = (grow < mvg && gcol < nvg) ? *reinterpret_cast<const uint4*>(Rg_ + (size_t)srow * nvg + gcol)
+                                                            : make_uint4(0u, 0u, 0u, 0u);
+                }
+        };
+        if constexpr (NEED_R) {
+            if (pair < nwork) load_r(pair, rnext);
+        }
         int chunk_i = 0;   // staging buffers alternate across tiles too: with BN = 128 a tile is ONE chunk per warp, and the bulk store of
                            // the previous tile may still be reading the other buffer (tma_store_wait_read<1> leaves one in flight)
         for (int wk = pair; wk < nwork; wk += npairs, lt++) {
@@ -233,6 +265,17 @@ gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
             uint16_t* const Cg = p.C[g];
             const uint16_t* const Rg = p.R[g];
             float* const Cfg = (EPI == G2_EPI_ATOMIC_F32) ? p.Cf + (size_t)g * p.M * p.N : nullptr;
+            // Residual operand of the epilogue (ADD / RELUSQ_BWD / BIAS_ADD / ACT_BWD): this warp's 32 x 64 tiles are fetched
+            // with row-contiguous accesses (8 lanes x 16 bytes = one 128-byte line per row, 4 rows per instruction) before the
+            // wait for the accumulator, and pass through the staging tile to the lane that owns the row.  (One 16-byte load per
+            // lane from 32 different rows made the relu^2-backward GEMM 3.4x slower than its forward twin: 198 vs 59 us.)
+            if constexpr (NEED_R) {
+#pragma unroll
+                for (int ch = 0; ch < NCH; ch++)
+#pragma unroll
+                    for (int k = 0; k < 8; k++) rpre[ch][k] = rnext[ch][k];
+                if (wk + npairs < nwork) load_r(wk + npairs, rnext);   // one tile ahead: in flight during this tile's epilogue
+            }
             mbar_wait(&sm.tmem_full[acc], (lt / NACC) & 1);
             tc_fence_after();
             // Plain results leave through shared memory and TMA stores (full 128-byte lines per row): 32 lanes writing 16 bytes
@@ -244,6 +287,15 @@ gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
                 uint8_t* const stile = &sm.stg[warp - 2][chunk_i & 1][0];
                 if (via_tma) {
                     if (g2_elect()) tma_store_wait_read<1>();   // the store that read this staging tile two chunks ago is done
+                    __syncwarp();
+                }
+                if constexpr (NEED_R) {
+                    const int ch = (c64 - half * (BN / 2)) >> 6;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const int rt = 4 * k + (lane >> 3);
+                        *reinterpret_cast<uint4*>(stile + rt * 128 + (((lane & 7) ^ (rt & 7)) << 4)) = rpre[ch][k];
+                    }
                     __syncwarp();
                 }
 #pragma unroll
@@ -266,19 +318,14 @@ gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
                         uint32_t* o = reinterpret_cast<uint32_t*>(out);
                         uint4 bia[4];
                         const bool inb = row < p.mv[g];
-                        if (EPI == G2_EPI_ADD || EPI == G2_EPI_RELUSQ_BWD || EPI == G2_EPI_ACT_BWD) {
+                        if constexpr (NEED_R) {
 #pragma unroll
                             for (int i = 0; i < 4; i++)
-                                res[i] = (inb && n0 + c + 8 * i < nvg) ? *reinterpret_cast<const uint4*>(Rg + offr + 8 * i) : make_uint4(0u, 0u, 0u, 0u);
+                                res[i] = *reinterpret_cast<const uint4*>(stile + lane * 128 + (((4 * sub + i) ^ (lane & 7)) << 4));
                         }
                         if (EPI == G2_EPI_BIAS || EPI == G2_EPI_BIAS_GELU || EPI == G2_EPI_BIAS_ADD) {
 #pragma unroll
                             for (int i = 0; i < 4; i++) bia[i] = (n0 + c + 8 * i < nvg) ? __ldg(reinterpret_cast<const uint4*>(p.bias[g] + n0 + c + 8 * i)) : make_uint4(0u, 0u, 0u, 0u);
-                            if (EPI == G2_EPI_BIAS_ADD) {
-                                const size_t roff = (size_t)(p.r_rows ? row % p.r_rows : row) * nvg + n0 + c;
-#pragma unroll
-                                for (int i = 0; i < 4; i++) res[i] = (inb && n0 + c + 8 * i < nvg) ? *reinterpret_cast<const uint4*>(Rg + roff + 8 * i) : make_uint4(0u, 0u, 0u, 0u);
-                            }
                         }
                         const uint32_t* bb = reinterpret_cast<const uint32_t*>(bia);
                         const uint32_t* rr = reinterpret_cast<const uint32_t*>(res);
@@ -322,8 +369,10 @@ gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
                                 else if (ac == 2) { x0 *= (1.f - h0) * h0; x1 *= (1.f - h1) * h1; }
                             } else if (EPI == G2_EPI_RELUSQ_BWD) {
                                 // eager graph: dact -> bf16, then d/dx relu(x)^2 = 2 relu(x) = 2 sqrt(act)
-                                x0 = __bfloat162float(__float2bfloat16_rn(x0)) * 2.f * sqrtf(bf16lo_to_f32(rr[i]));
-                                x1 = __bfloat162float(__float2bfloat16_rn(x1)) * 2.f * sqrtf(bf16hi_to_f32(rr[i]));
+                                // MUFU sqrt: the IEEE sqrtf of a non-fast-math build is a ~30-instruction routine per element and made
+                                // this epilogue 2.5x the tile's tensor-core time (dev_gemm2_epi: 152 vs 60 us)
+                                x0 = __bfloat162float(__float2bfloat16_rn(x0)) * 2.f * g2_sqrt(bf16lo_to_f32(rr[i]));
+                                x1 = __bfloat162float(__float2bfloat16_rn(x1)) * 2.f * g2_sqrt(bf16hi_to_f32(rr[i]));
                             }
                             o[i] = pack_bf16x2(x0, x1);
                         }

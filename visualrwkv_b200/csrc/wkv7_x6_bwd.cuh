@@ -134,6 +134,7 @@ wkv7_x3_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
     __syncwarp();
 
     uint32_t ph_in = 0, ph_dy = 0, ph_v = 0, ph_mma = 0, ph_c3 = 0;
+#ifdef VRWKV_PHASE_STAMPS   // development aid (scripts/dbg_x6_stamps.py, dbg_x3_stamps.py): build with VRWKV_PHASE_STAMPS=1
     float* const dbg = (blockIdx.x == 0 && tid == 0) ? g_chunk_dbg : nullptr;
     int lt = 0, tsi = 0;
     long long tstamp0 = 0;
@@ -144,6 +145,10 @@ wkv7_x3_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
             dbg[3072 + tsi++] = (float)(now - tstamp0);
         }
     };
+#else
+    int lt = 0;
+    auto stamp = [] {};
+#endif
     auto mma_wait = [&]() {
         mbar_wait(&sm.bar_mma, ph_mma & 1);
         ph_mma++;

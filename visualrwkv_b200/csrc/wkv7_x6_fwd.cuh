@@ -119,6 +119,7 @@ wkv7_x6_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
 
     uint32_t ph_in = 0, ph_v = 0, ph_mma = 0;
     // development aid (vrwkv_wkv7_chunk_debug): CTA 0 records the clock at every phase boundary of its third item
+#ifdef VRWKV_PHASE_STAMPS   // development aid (scripts/dbg_x6_stamps.py, dbg_x3_stamps.py): build with VRWKV_PHASE_STAMPS=1
     float* const dbg = (blockIdx.x == 0 && tid == 0) ? g_chunk_dbg : nullptr;
     int lt = 0, tsi = 0;
     long long tstamp0 = 0;
@@ -129,6 +130,10 @@ wkv7_x6_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
             dbg[2048 + tsi++] = (float)(now - tstamp0);
         }
     };
+#else
+    int lt = 0;
+    auto stamp = [] {};
+#endif
     auto mma_wait = [&]() {
         mbar_wait(&sm.bar_mma, ph_mma & 1);
         ph_mma++;
