@@ -272,3 +272,60 @@ def test_fused_adamw_matches_torch_adamw():
     g.replay()
     torch.cuda.synchronize()
     assert int(opt.step_count) == before + 1
+
+
+def test_recurrent_forward_split_sequence_equivalence():
+    """prefill + stateful continuation equals one pass over the whole sequence (no reference oracle for
+    this row): 128 tokens at once (chunked tensor-core WKV7) vs 64 + 64 vs 127 + 1 (step-by-step kernel, T = 1 decode with
+    M = 2 GEMMs), and vs the stateless training-path forward."""
+    from visualrwkv_b200.recurrent import rwkv_forward_recurrent
+    m, args = _tiny(seed=2, T=128)
+    torch.manual_seed(5)
+    x = (0.5 * torch.randn(2, 128, args.n_embd, device="cuda")).to(torch.bfloat16)
+    with torch.no_grad():
+        ref = m.rwkv(x)                                              # stateless path, [2,128,V]
+    full, st_full = rwkv_forward_recurrent(m.rwkv, x, last_only=False)
+    assert _rel(full, ref) < 2e-2
+    for cut in (64, 127, 16):
+        a, st = rwkv_forward_recurrent(m.rwkv, x[:, :cut].contiguous(), last_only=False)
+        b, st = rwkv_forward_recurrent(m.rwkv, x[:, cut:].contiguous(), st, last_only=False)
+        assert st.tokens_seen == 128
+        assert _rel(torch.cat([a, b], dim=1), full) < 2e-2, cut
+        for l0, l1 in zip(st.layers, st_full.layers):
+            assert _rel(l0.wkv, l1.wkv) < 2e-2, cut
+            assert _rel(l0.att_prev, l1.att_prev) < 2e-2 and _rel(l0.ffn_prev, l1.ffn_prev) < 2e-2
+    last, _ = rwkv_forward_recurrent(m.rwkv, x)
+    assert last.shape == (2, args.vocab_size) and _rel(last, full[:, -1]) < 1e-3
+
+
+def test_recurrent_generate_matches_stateless_loop():
+    """VisualRWKV.generate(recurrent=True): first token from the same prompt logits as the reference-style loop (prompt
+    length a multiple of 16, so the loop's left padding is empty), then five single-token steps (B = 1, T = 1)."""
+    m, args = _tiny(seed=3, T=64)
+    batch = MR.make_batch(1, 64, 16, 64, seed=7, device="cuda", img_dtype=torch.bfloat16, human_tokens=4)
+    ids, imgs = batch["input_ids"], batch["images"]
+    with torch.no_grad():
+        t_loop, l_loop, p_loop = m.generate(ids, imgs, False, 1.0, 1.0, 1, -1)
+    t_rec, l_rec, p_rec = m.generate(ids, imgs, False, 1.0, 1.0, 6, -1, recurrent=True)
+    assert len(t_rec) == 6 and all(0 <= t < args.vocab_size for t in t_rec)
+    assert abs(l_rec[0] - l_loop[0]) < 2e-2 * max(1.0, abs(l_loop[0]))
+    assert t_rec[0] == t_loop[0] or abs(l_rec[0] - l_loop[0]) < 1e-2
+
+
+def test_graphed_decoder_matches_eager_decode():
+    """GraphedDecoder (one CUDA graph per T = 1 step, state updated in place) against eager recurrent steps."""
+    from visualrwkv_b200.recurrent import GraphedDecoder, rwkv_forward_recurrent
+    m, args = _tiny(seed=4, T=64)
+    torch.manual_seed(6)
+    x = (0.5 * torch.randn(3, 48, args.n_embd, device="cuda")).to(torch.bfloat16)
+    toks = torch.randint(0, 60000, (4, 3, 1), device="cuda")
+    _, st_e = rwkv_forward_recurrent(m.rwkv, x)
+    _, st_g = rwkv_forward_recurrent(m.rwkv, x)
+    dec = GraphedDecoder(m, st_g, 3)
+    for t in toks:
+        le, st_e = rwkv_forward_recurrent(m.rwkv, m.rwkv.emb(t).to(torch.bfloat16), st_e)
+        lg = dec.step(t)
+        assert _rel(lg, le) < 1e-3
+    assert st_g.tokens_seen == st_e.tokens_seen == 52
+    for a, b in zip(st_g.layers, st_e.layers):
+        assert _rel(a.wkv, b.wkv) < 1e-3 and torch.equal(a.att_prev, b.att_prev)

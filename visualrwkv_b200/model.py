@@ -333,9 +333,16 @@ class VisualRWKV(_Base):
         return ops.head_loss(feats.contiguous(), self.rwkv.head.weight, targets, IGNORE_INDEX)
 
     @torch.no_grad()
-    def generate(self, input_ids, images, do_sample, temperature, top_p, max_new_tokens, stop_token_idx):
-        """model.py:496-530 (greedy only, as the reference).  Re-runs the full sequence per token like the
-        reference does; the O(1)/token stateful path is SURVEY.md §8f-2."""
+    def generate(self, input_ids, images, do_sample, temperature, top_p, max_new_tokens, stop_token_idx, recurrent=False):
+        """model.py:496-530 (greedy only, as the reference).  Default: re-runs the full sequence per token exactly like the
+        reference (left-padded to a multiple of 16 each time).  recurrent=True: the prompt is processed once and every new
+        token is one stateful step (visualrwkv_b200/recurrent.py) — same arithmetic without the per-call
+        left padding."""
+        if recurrent:
+            if do_sample:
+                raise NotImplementedError
+            from .recurrent import generate_recurrent
+            return generate_recurrent(self, input_ids, images, max_new_tokens, stop_token_idx)
         samples = {"input_ids": input_ids, "images": images, "labels": torch.full_like(input_ids, IGNORE_INDEX)}
         x, _ = self.preparing_embedding(samples)
         toks, logits_l, probs_l = [], [], []

@@ -153,17 +153,24 @@ def RUN_CUDA_RWKV7g(q, w, k, v, a, b, bounded_decay: bool = False):
     return fn.apply(w, q, k, v, a, b).view(B, T, HC)
 
 
-def wkv7_forward_state(w, q, k, v, a, b, state_in=None, want_checkpoints: bool = False):
+def wkv7_forward_state(w, q, k, v, a, b, state_in=None, want_checkpoints: bool = False, bounded_decay: bool = False,
+                       state_out=None):
     """Stateful forward: returns (y, state_out[, s, sa]); inference only (no grad).
 
     state_in / state_out: f32 [B,H,64,64] (S_ij row-major).  T need not be a multiple of 16 unless
-    checkpoints are requested.
+    checkpoints are requested.  bounded_decay=True (the caller's promise exp(w) <= 0.607, see forward_raw) lets a
+    prefill whose T is a multiple of 64 run on the chunked tensor-core kernel; any other T (the T = 1 decode step
+    included) runs on the step-by-step kernel either way.  state_out may be given (and, for T % 64 != 0, may be state_in
+    itself: the step-by-step kernel reads a head's state once at the start and writes it once at the end).
     """
     L = _lib.lib()
     B, T, H, C = w.shape
     assert C == 64 and all(i.dtype == torch.bfloat16 and i.is_contiguous() and i.is_cuda for i in [w, q, k, v, a, b])
     y = torch.empty_like(v)
-    state_out = torch.empty(B, H, C, C, dtype=torch.float32, device=w.device)
+    if state_out is None:
+        state_out = torch.empty(B, H, C, C, dtype=torch.float32, device=w.device)
+    assert state_out.dtype == torch.float32 and state_out.is_contiguous() and state_out.shape == (B, H, C, C)
+    assert state_out is not state_in or T % CHUNK != 0 or not bounded_decay, "in-place state only on the step-by-step kernel"
     s = sa = None
     if want_checkpoints:
         s = torch.empty(B, H, T // CHUNK_LEN, C, C, dtype=torch.float32, device=w.device)
@@ -171,10 +178,11 @@ def wkv7_forward_state(w, q, k, v, a, b, state_in=None, want_checkpoints: bool =
     if state_in is not None:
         assert state_in.dtype == torch.float32 and state_in.is_contiguous() and state_in.shape == (B, H, C, C)
     with torch.cuda.device(w.device):
-        rc = L.vrwkv_wkv7_forward_state(B, T, H, _lib.ptr(w), _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(a),
-                                        _lib.ptr(b), _lib.ptr(y), _lib.ptr(s), _lib.ptr(sa), _lib.ptr(state_in),
-                                        _lib.ptr(state_out), _lib.cur_stream())
-    _lib.check(rc, "vrwkv_wkv7_forward_state")
+        rc = L.vrwkv_wkv7_forward_ex(B, T, H, _lib.ptr(w), _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(a),
+                                     _lib.ptr(b), _lib.ptr(y), _lib.ptr(s), _lib.ptr(sa), _lib.ptr(state_in),
+                                     _lib.ptr(state_out), _flags(bool(bounded_decay and T % CHUNK == 0), False, False),
+                                     _lib.cur_stream())
+    _lib.check(rc, "vrwkv_wkv7_forward_ex")
     return (y, state_out, s, sa) if want_checkpoints else (y, state_out)
 
 
