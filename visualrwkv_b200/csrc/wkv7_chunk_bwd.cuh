@@ -100,12 +100,16 @@ wkv7_chunk_bwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
     }
     __syncwarp();
 
+#ifdef VRWKV_PHASE_STAMPS   // development builds only (VRWKV_PHASE_STAMPS=1): per-phase clocks of chunk 1 of CTA (0,0)
     float* const dbg = (hh == 0 && bb == 0 && c == 1) ? g_chunk_dbg : nullptr;
     const long long tstamp0 = clock64();
     int tsi = 0;
     auto stamp = [&]() {
         if (dbg && tid == 0) dbg[3072 + tsi++] = (float)(clock64() - tstamp0);
     };
+#else
+    auto stamp = [] {};
+#endif
     {   // the delta phase reads U (= sa rows) and S_0 from global memory: start pulling them into L2 now
         const int t = tid >> 3, i0 = 8 * (tid & 7);
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p.sa + row0 + (size_t)t * rstride + i0));

@@ -97,7 +97,9 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
     };
     if (tid == 0) issue_loads(0);
     __syncwarp();
+#ifdef VRWKV_PHASE_STAMPS   // development builds only (VRWKV_PHASE_STAMPS=1)
     float* const dbg = (hh == 0 && bb == 0) ? g_chunk_dbg : nullptr;
+#endif
 
     // ---- initial state: fp32 in registers (thread r < 64 holds S[r][16cs .. 16cs+15]) + tf32 image as B operand ----
     float Sprev[16];
@@ -124,6 +126,7 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
     __syncthreads();
     tc_fence_after();
 
+#ifdef VRWKV_PHASE_STAMPS
     long long tstamp0 = 0;
     int tsi = 0;
     auto stamp = [&](int c) {
@@ -133,6 +136,9 @@ wkv7_chunk_fwd_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_con
             dbg[2048 + tsi++] = (float)(now - tstamp0);
         }
     };
+#else
+    auto stamp = [](int) {};
+#endif
     uint32_t mph = 0;  // phase of bar_mma (every commit is waited for before the next one is issued)
     auto mma_wait = [&](int c) {
         stamp(c);

@@ -455,7 +455,8 @@ class HeadLossFn(torch.autograd.Function):
         loss = (nll.view(B, T).sum(1) / valid).mean()
         ctx.save_for_backward(x2, weight, logits, labels, lse, rmax, amax, valid)
         ctx.meta = (B, T, C, V, ignore_index)
-        return loss.to(x.dtype)
+        ctx.logits_consumed = False
+        return loss.to(x.dtype)   # the reference's F.cross_entropy on bf16 logits returns a bf16 loss too (model.py:430-434)
 
     @staticmethod
     def backward(ctx, gloss):
@@ -463,6 +464,12 @@ class HeadLossFn(torch.autograd.Function):
         x2, weight, logits, labels, lse, rmax, amax, valid = ctx.saved_tensors
         B, T, C, V, ignore_index = ctx.meta
         rows = B * T
+        if ctx.logits_consumed:
+            # the first backward turned the saved logits into d(loss)/d(logits) in place (one buffer of B*T*V bf16 instead of
+            # two); a second pass over the same graph (retain_graph=True) would read gradients as logits
+            raise RuntimeError("HeadLossFn: backward called twice on the same forward (the logits buffer was reused for the "
+                               "gradient); run the forward again instead of retain_graph=True")
+        ctx.logits_consumed = True
         has_t = torch.ones(B, T, dtype=torch.bool, device=x2.device)
         has_t[:, -1] = False
         has_t[:, :-1] &= labels[:, 1:] != ignore_index

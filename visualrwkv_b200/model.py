@@ -193,6 +193,10 @@ class RWKV(_Base):
     def __init__(self, args):
         super().__init__()
         self.args = args
+        if args.n_embd % 64 or args.n_embd > 2048:
+            # the fused row kernels keep a row's channels in one CTA / warp (csrc/fused_ln.cu, fused_tmix.cu): 0.1B .. 1.5B
+            # (n_embd 768 .. 2048) are covered; RWKV-7 2.9B (n_embd 2560) is not
+            raise ValueError(f"visualrwkv_b200: n_embd={args.n_embd} must be a multiple of 64 and <= 2048")
         self.emb = nn.Embedding(args.vocab_size, args.n_embd)
         self.blocks = nn.ModuleList([Block(args, i) for i in range(args.n_layer)])
         self.ln_out = nn.LayerNorm(args.n_embd)
