@@ -179,10 +179,10 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        r = cpu_reference_run(max(a.steps, 5), a.warmup)
+        r = cpu_reference_run(max(a.steps, 1), a.warmup)
         config["reference_sample"] = r["sample"]   # what one timed step of this arm actually is (a bounded sample of the workload)
         line = {"impl": "reference", "metric": "tokens/s fwd+bwd (T=2048, 576 img-tok)", "value": r["value"], "unit": "tokens/s",
-                "n_gpus": a.gpus, "steps": max(a.steps, 5), "warmup": a.warmup, "ms_per_step": r["ms_per_step"],
+                "n_gpus": a.gpus, "steps": max(a.steps, 1), "warmup": a.warmup, "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config, "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu")},
                 "e2e": {"value": r["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
