@@ -401,9 +401,6 @@ __global__ void __launch_bounds__(MAXT) ln_mix_bwd_kernel(const LnMixBwdArgs a) 
 constexpr int WR_RUN = 8;      // rows per warp (16: half the warps, and the kernels are latency-bound at ~7 warps per SM)
 constexpr int WR_WARPS = 4;    // warps per CTA  -> 32 rows per CTA
 
-__device__ __forceinline__ uint32_t bf2_sub(uint32_t a, uint32_t b) { uint32_t r; asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
-__device__ __forceinline__ uint32_t bf2_mul(uint32_t a, uint32_t b) { uint32_t r; asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
-__device__ __forceinline__ uint32_t bf2_add(uint32_t a, uint32_t b) { uint32_t r; asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ uint32_t& w4(uint4& v, int i) { return reinterpret_cast<uint32_t*>(&v)[i]; }
 __device__ __forceinline__ uint32_t w4(const uint4& v, int i) { return reinterpret_cast<const uint32_t*>(&v)[i]; }
 

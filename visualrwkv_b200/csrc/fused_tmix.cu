@@ -43,13 +43,20 @@ struct TmixMidArgs {
     float* partial;  // [grid][5][C]: dw0, da0, dv0, dk_k, dk_a
 };
 
+__device__ __forceinline__ uint32_t& u4(uint4& v, int i) { return reinterpret_cast<uint32_t*>(&v)[i]; }
+__device__ __forceinline__ uint32_t u4(const uint4& v, int i) { return reinterpret_cast<const uint32_t*>(&v)[i]; }
+
+// The chain of bf16 element-wise ops of model.py:176-190 runs in packed bf16x2 arithmetic (rowops.cuh: one rounding per
+// op, as the eager graph), two channels per instruction; only softplus / sigmoid / the head norm go through fp32.  The
+// fp32 version of this kernel spent ~120 issue slots per element on convert-and-shift round trips (ncu: 42 % issue at
+// 18 % occupancy, 2.9 TB/s).
 __global__ void __launch_bounds__(256) tmix_mid_fwd_kernel(const TmixMidArgs a) {
     const int c0 = threadIdx.x * 8;
     const bool active = c0 < a.C;
-    const F8 w0 = ldz(active, a.w0 + c0), a0 = ldz(active, a.a0 + c0), kk_ = ldz(active, a.k_k + c0), ka = ldz(active, a.k_a + c0);
-    F8 v0 = zero8();
-    if (a.has_vres) v0 = ldz(active, a.v0 + c0);
+    const uint4 w0 = ldraw(active, a.w0 + c0), a0 = ldraw(active, a.a0 + c0), kk_ = ldraw(active, a.k_k + c0), ka = ldraw(active, a.k_a + c0);
+    const uint4 v0 = ldraw(active && a.has_vres, a.v0 + c0);
     const int row0 = blockIdx.x * TM_RUN, row1 = min(row0 + TM_RUN, a.rows);
+    constexpr uint32_t ONE2 = 0x3F803F80u, HALF2 = 0x3F003F00u, SIGN2 = 0x80008000u;
     // software pipeline: the loads of row+1 are issued before row is computed and stored
     struct In { uint4 k, v, ww, aa, vf, vv; };
     auto load = [&](int row) {
@@ -65,38 +72,46 @@ __global__ void __launch_bounds__(256) tmix_mid_fwd_kernel(const TmixMidArgs a) 
         const size_t o = (size_t)row * a.C + c0;
         const In cur = nxt;
         nxt = load(row + 1);
-        const F8 k = f8(cur.k), v = f8(cur.v), ww = f8(cur.ww), aa = f8(cur.aa);
-        F8 ow, ok, ov, onkk, okka, u, av;
+        uint4 ow, ok, ov, onkk, okka, u, av;
         float ss = 0.f;
 #pragma unroll
-        for (int e = 0; e < 8; e++) {
-            const float z = rb(w0.v[e] + ww.v[e]);
-            ow.v[e] = -rb(softplusf_(-z)) - 0.5f;
-            av.v[e] = rb(sigmoidf_(rb(a0.v[e] + aa.v[e])));
-            u.v[e] = rb(k.v[e] * kk_.v[e]);
-            ss += u.v[e] * u.v[e];
-            ok.v[e] = k.v[e] * rb(1.f + rb(rb(av.v[e] - 1.f) * ka.v[e]));
-        }
-        if (a.has_vres) {
-            const F8 vf = f8(cur.vf), vv = f8(cur.vv);
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-                const float vg = rb(sigmoidf_(rb(v0.v[e] + vv.v[e])));
-                ov.v[e] = v.v[e] + rb(rb(vf.v[e] - v.v[e]) * vg);
+        for (int i = 0; i < 4; i++) {
+            // w = -softplus(-(w0 + ww)) - 0.5
+            const uint32_t z = bf2_add(u4(w0, i), u4(cur.ww, i));
+            const uint32_t sp = pack_bf16x2(softplusf_(-bf16lo_to_f32(z)), softplusf_(-bf16hi_to_f32(z)));
+            u4(ow, i) = bf2_sub(sp ^ SIGN2, HALF2);
+            // a = sigmoid(a0 + aa)
+            const uint32_t za = bf2_add(u4(a0, i), u4(cur.aa, i));
+            const uint32_t avp = pack_bf16x2(sigmoidf_(bf16lo_to_f32(za)), sigmoidf_(bf16hi_to_f32(za)));
+            u4(av, i) = avp;
+            // u = k * k_k (normalised below);  k' = k * (1 + (a - 1) * k_a)
+            const uint32_t up = bf2_mul(u4(cur.k, i), u4(kk_, i));
+            u4(u, i) = up;
+            const float u0 = bf16lo_to_f32(up), u1 = bf16hi_to_f32(up);
+            ss = fmaf(u0, u0, ss);
+            ss = fmaf(u1, u1, ss);
+            u4(ok, i) = bf2_mul(u4(cur.k, i), bf2_add(ONE2, bf2_mul(bf2_sub(avp, ONE2), u4(ka, i))));
+            // v' = v + (v_first - v) * sigmoid(v0 + vv)      (layers > 0)
+            if (a.has_vres) {
+                const uint32_t zv = bf2_add(u4(v0, i), u4(cur.vv, i));
+                const uint32_t vg = pack_bf16x2(sigmoidf_(bf16lo_to_f32(zv)), sigmoidf_(bf16hi_to_f32(zv)));
+                u4(ov, i) = bf2_add(u4(cur.v, i), bf2_mul(bf2_sub(u4(cur.vf, i), u4(cur.v, i)), vg));
+            } else {
+                u4(ov, i) = u4(cur.v, i);
             }
-        } else {
-            ov = v;
         }
         const float nrm = fmaxf(rb(sqrtf(head_sum(ss))), 1e-12f);  // F.normalize(p=2, eps=1e-12)
         const float inrm = 1.f / nrm;
 #pragma unroll
-        for (int e = 0; e < 8; e++) {
-            const float kk = rb(u.v[e] * inrm);
-            onkk.v[e] = -kk;
-            okka.v[e] = kk * av.v[e];
+        for (int i = 0; i < 4; i++) {
+            const uint32_t kk = pack_bf16x2(bf16lo_to_f32(u4(u, i)) * inrm, bf16hi_to_f32(u4(u, i)) * inrm);
+            u4(onkk, i) = kk ^ SIGN2;
+            u4(okka, i) = bf2_mul(kk, u4(av, i));
         }
-        stz(active, a.w + o, ow); stz(active, a.k2 + o, ok); stz(active, a.v2 + o, ov);
-        stz(active, a.nkk + o, onkk); stz(active, a.kka + o, okka);
+        if (active) {
+            *reinterpret_cast<uint4*>(a.w + o) = ow; *reinterpret_cast<uint4*>(a.k2 + o) = ok; *reinterpret_cast<uint4*>(a.v2 + o) = ov;
+            *reinterpret_cast<uint4*>(a.nkk + o) = onkk; *reinterpret_cast<uint4*>(a.kka + o) = okka;
+        }
     }
 }
 
