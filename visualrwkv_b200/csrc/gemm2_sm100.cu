@@ -514,7 +514,15 @@ extern "C" int vrwkv_gemm2_bf16_grouped(int M, int N, int K, int ngroups, const 
     const bool need_r = epilogue == G2_EPI_ADD || epilogue == G2_EPI_RELUSQ_BWD || epilogue == G2_EPI_BIAS_ADD || epilogue == G2_EPI_ACT_BWD;
     const bool need_b = epilogue >= G2_EPI_BIAS && epilogue <= G2_EPI_BIAS_ADD;
     if (need_b && (layout != 0 || !bias)) return vrwkv_fail(VRWKV_EINVAL, "gemm2: bias epilogues need the [M,K] x [N,K] layout and a bias per group");
-    const int BN = (N % 256 == 0) ? 256 : 128;
+    int BN = (N % 256 == 0) ? 256 : 128;
+    // Weight gradients whose 256-wide tiling leaves most CTA pairs idle (the four C x C gradients of a time-mix block: 36
+    // tiles for 74 pairs) run better as twice as many 128-wide tiles than as two contraction slices meeting in fp32 atomics:
+    // the split pays a fixed ~35 us per launch for the atomics to drain, the ticket and the last slice's conversion
+    // (dev_lora.py: T(k-blocks) = 37 us + 0.19 us per k-block).
+    if (BN == 256 && ksplit == 1 && a_mn && b_mn) {
+        const int tiles256 = ngroups * ((M + 2 * G2_BM - 1) / (2 * G2_BM)) * (N / 256);
+        if (tiles256 < 60) BN = 128;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     Gemm2Maps maps;
     Gemm2Args a{};

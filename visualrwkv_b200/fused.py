@@ -572,8 +572,12 @@ def _lora_ok(*downs):
 
 
 def _ksplit(groups, M, N, K):
-    """Slices of the contraction for a weight gradient: enough (group, tile, slice) items for the 74 CTA pairs."""
+    """Slices of the contraction for a weight gradient: enough (group, tile, slice) items for the 74 CTA pairs.  When
+    halving the tile width (the C library does that by itself for an unsplit weight gradient with fewer than 60 tiles)
+    already fills the machine, no split: the fp32-atomic meeting of slices costs a fixed ~35 us per launch."""
     tiles = groups * ((M + 255) // 256) * (N // (256 if N % 256 == 0 else 128))
+    if N % 256 == 0 and tiles < 60 and 2 * tiles >= 60:
+        return 1
     ks = 1
     while ks < 8 and tiles * ks < 74 and K % (64 * ks * 2) == 0:
         ks *= 2
