@@ -417,15 +417,23 @@ gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
                     if (lane == 0) *ticket = 0;
                     if (row < p.M) {
                         const int mvg = p.mv[g], nvg = p.nv[g];
+                        // 32 columns per trip with all eight loads issued first: one L2 round trip per 128 bytes of a row instead of
+                        // one per 32 bytes (this tail is part of the fixed cost of a split launch)
 #pragma unroll 1
-                        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 8) {
+                        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
                             float4* src = reinterpret_cast<float4*>(Cfg + (size_t)row * p.N + n0 + c);
-                            const float4 x = __ldcg(src), y = __ldcg(src + 1);
-                            uint4 o;
-                            o.x = pack_bf16x2(x.x, x.y); o.y = pack_bf16x2(x.z, x.w); o.z = pack_bf16x2(y.x, y.y); o.w = pack_bf16x2(y.z, y.w);
-                            if (row < mvg && n0 + c < nvg) *reinterpret_cast<uint4*>(Cg + (size_t)row * nvg + n0 + c) = o;
-                            src[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            src[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            float4 x[8];
+#pragma unroll
+                            for (int i = 0; i < 8; i++) x[i] = __ldcg(src + i);
+#pragma unroll
+                            for (int i = 0; i < 4; i++) {
+                                uint4 o;
+                                o.x = pack_bf16x2(x[2 * i].x, x[2 * i].y); o.y = pack_bf16x2(x[2 * i].z, x[2 * i].w);
+                                o.z = pack_bf16x2(x[2 * i + 1].x, x[2 * i + 1].y); o.w = pack_bf16x2(x[2 * i + 1].z, x[2 * i + 1].w);
+                                if (row < mvg && n0 + c + 8 * i < nvg) *reinterpret_cast<uint4*>(Cg + (size_t)row * nvg + n0 + c + 8 * i) = o;
+                                src[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                src[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
                         }
                     }
                 }
