@@ -178,7 +178,7 @@ int vrwkv_gemm_bf16_tn(int M, int N, int K, const uint16_t* A, const uint16_t* B
  * 5 + bias[g][n], 6 tanh-GELU(. + bias), 7 . + bias + R[g][row % r_rows] (the SigLIP tower's Linear layers),
  * 8 act[g](.) with act 0 none / 1 tanh / 2 sigmoid, 9 (.) * act[g]'(R[g]) from the saved output (the LoRA branches).
  * ksplit > 1 slices the contraction (weight gradients over the 16384 token rows): slices meet in an internal fp32
- * workspace and the last one writes the bf16 result; c_transposed[g] != 0 stores C[g] as [N,M].
+ * workspace and the last one writes the bf16 result; c_transposed[g] != 0 stores C[g] as [N,M] (plain epilogue only).
  * K % (64 ksplit) == 0, N % 128 == 0, M % 8 == 0 for layout bit 0.
  * dims (optional, 3 ints per group: Mg, Ng, Kg <= M, N, K, multiples of 8): the group's tensors are exactly that
  * large (row strides Mg/Ng/Kg); the launch tiles (M, N, K) and the loads zero-fill / the stores clip beyond them, so

@@ -59,3 +59,6 @@ def lib_bwd():
 
 
 print("library fwd %.4f  bwd %.4f" % (timeit(lib_fwd), timeit(lib_bwd)))
+for ks in (2, 4):
+    print("dU^T (dout^T h) ks=%d  %.4f" % (ks, timeit(lambda: fused.gemm2_grouped(douts, hs, fused.G2_TT, ksplit=ks))))
+print("dU^T ks=4 + 4 transposes  %.4f" % timeit(lambda: [t.t().contiguous() for t in fused.gemm2_grouped(douts, hs, fused.G2_TT, ksplit=4)]))

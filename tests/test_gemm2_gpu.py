@@ -96,6 +96,10 @@ def test_lora_branch_shapes(rows, C, ranks):
     for dx, dp, d in zip(dxs, dps, downs):
         assert rel(dx, dp.float() @ d.float().t()) < 2.5e-3
     Rp = max(ranks)
+    for ks in (1, 2):   # transposed store from a split contraction (the LoRA up-weight gradient as (dout^T h)^T)
+        dUt = fused.gemm2_grouped(douts, hs, fused.G2_TT, ksplit=ks, transposed=[1] * len(ranks))
+        for g, h, do, r in zip(dUt, hs, douts, ranks):
+            assert g.shape == (r, C) and rel(g, h.float().t() @ do.float()) < 2.5e-3
     for ks in (1, fused._ksplit(len(ranks), Rp, C, rows)):
         dU = fused.gemm2_grouped(hs, douts, fused.G2_TT, ksplit=ks)
         dD = fused.gemm2_grouped(xs, dps, fused.G2_TT, ksplit=ks)

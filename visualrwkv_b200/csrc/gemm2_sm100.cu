@@ -430,7 +430,16 @@ gemm2_kernel(const __grid_constant__ Gemm2Maps maps, const Gemm2Args p) {
                                 uint4 o;
                                 o.x = pack_bf16x2(x[2 * i].x, x[2 * i].y); o.y = pack_bf16x2(x[2 * i].z, x[2 * i].w);
                                 o.z = pack_bf16x2(x[2 * i + 1].x, x[2 * i + 1].y); o.w = pack_bf16x2(x[2 * i + 1].z, x[2 * i + 1].w);
-                                if (row < mvg && n0 + c + 8 * i < nvg) *reinterpret_cast<uint4*>(Cg + (size_t)row * nvg + n0 + c + 8 * i) = o;
+                                if (p.ct[g]) {   // C^T: consecutive lanes (rows) write consecutive bf16 of one output row
+                                    const uint16_t* o16 = reinterpret_cast<const uint16_t*>(&o);
+#pragma unroll
+                                    for (int e = 0; e < 8; e++) {
+                                        const int col = n0 + c + 8 * i + e;
+                                        if (row < mvg && col < nvg) Cg[(size_t)col * mvg + row] = o16[e];
+                                    }
+                                } else if (row < mvg && n0 + c + 8 * i < nvg) {
+                                    *reinterpret_cast<uint4*>(Cg + (size_t)row * nvg + n0 + c + 8 * i) = o;
+                                }
                                 src[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
                                 src[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
                             }
@@ -566,7 +575,7 @@ extern "C" int vrwkv_gemm2_bf16_grouped(int M, int N, int K, int ngroups, const 
         a.ct[g] = (c_transposed && c_transposed[g]) ? 1 : 0;
         a.bias[g] = need_b ? bias[g] : nullptr;
         a.act[g] = act ? act[g] : 0;
-        if (a.ct[g] && (epilogue != G2_EPI_NONE || ksplit > 1)) return vrwkv_fail(VRWKV_EINVAL, "gemm2: transposed store only with the plain epilogue");
+        if (a.ct[g] && epilogue != G2_EPI_NONE) return vrwkv_fail(VRWKV_EINVAL, "gemm2: transposed store only with the plain epilogue");
     }
     for (int g = ngroups; g < G2_MAXG; g++) { maps.a[g] = maps.a[0]; maps.b[g] = maps.b[0]; maps.c[g] = maps.c[0]; }
     int epi = epilogue;

@@ -313,7 +313,9 @@ class TmixBlockFn(torch.autograd.Function):
             ng, Rp = len(hs), max(h.shape[1] for h in hs)
             dps = gemm2_grouped(douts, ups, G2_TN, EPI_ACT_BWD, residuals=hs, acts=acts)        # d(pre-activation) [rows, rank]
             dxl = gemm2_grouped(dps, downs, G2_TN)                                              # [rows, C]
-            dU = gemm2_grouped(hs, douts, G2_TT, ksplit=min(4, _ksplit(ng, Rp, C, rows)))       # h^T dout [rank, C]
+            # h^T dout [rank, C], computed as (dout^T h)^T: with the rank as the M extent half of every 256-row pair tile is
+            # padding and the launch ran 1.6x (warm) to 3x (cold) slower than its mirror image below (scripts/dev_lora.py)
+            dU = gemm2_grouped(douts, hs, G2_TT, ksplit=min(4, _ksplit(ng, C, Rp, rows)), transposed=[1] * ng)
             dD = gemm2_grouped(xs, dps, G2_TT, ksplit=min(4, _ksplit(ng, C, Rp, rows)))         # x^T dpre [C, rank]
             dw2, da2, dg2 = dU[:3]
             dw1, da1, dg1 = dD[:3]
