@@ -130,7 +130,7 @@ def test_standalone_module_api():
 def test_layernorm_fn():
     from visualrwkv_b200 import fused
     torch.manual_seed(0)
-    for C in (128, 768, 1024):
+    for C in (128, 768, 1024, 1536, 2048):   # 1536 / 2048: warp-per-row forward with 6 / 8 vectors per lane, round-1 backward
         x = torch.randn(3, 40, C, device="cuda").to(torch.bfloat16).requires_grad_(True)
         w = (1 + 0.1 * torch.randn(C, device="cuda")).to(torch.bfloat16).requires_grad_(True)
         b = (0.1 * torch.randn(C, device="cuda")).to(torch.bfloat16).requires_grad_(True)
@@ -170,3 +170,24 @@ def test_token_shift_mix_is_bit_exact():
         one = torch.ones(C, device="cuda", dtype=torch.bfloat16)
         (o1,), _, _ = fused.ln_mix_forward(x.view(B * T, C), T, None, None, 1e-5, [one])
         assert torch.equal(o1.view(B, T, C)[:, 0], x[:, 0] + (torch.zeros_like(x[:, 0]) - x[:, 0]))
+
+
+@pytest.mark.parametrize("C", [1280, 2048])
+def test_ln_mix_forward_wide_rows_match_eager(C):
+    """LayerNorm + shift + six mixes at the widths of the 1.5B model (warp-per-row forward, 5..8 vectors per lane) against
+    the eager bf16 graph: ln -> shift -> x + xx * c."""
+    from visualrwkv_b200 import fused
+    torch.manual_seed(C)
+    B, T = 2, 48
+    x = torch.randn(B, T, C, device="cuda").to(torch.bfloat16)
+    g = (1 + 0.1 * torch.randn(C, device="cuda")).to(torch.bfloat16)
+    b = (0.1 * torch.randn(C, device="cuda")).to(torch.bfloat16)
+    coefs = [torch.rand(C, device="cuda").to(torch.bfloat16) for _ in range(6)]
+    outs, _, stats = fused.ln_mix_forward(x.view(B * T, C), T, g, b, 1e-5, coefs)
+    h = torch.nn.functional.layer_norm(x, (C,), g, b, 1e-5)
+    xx = torch.cat([torch.zeros_like(h[:, :1]), h[:, :-1]], dim=1) - h
+    for o, c in zip(outs, coefs):
+        ref = h + xx * c.view(1, 1, C)
+        assert _rel(o.view(B, T, C), ref.float()) < 4e-3
+    mean = x.float().mean(-1).reshape(-1)
+    assert torch.allclose(stats[:, 0], mean, atol=1e-4)

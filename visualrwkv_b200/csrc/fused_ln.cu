@@ -908,7 +908,8 @@ static int ln_check(int rows, int T, int C, int nmix) {
 
 extern "C" int vrwkv_ln_mix_blocks(int rows) { return (rows + LN_RUN - 1) / LN_RUN; }
 // number of partial rows the backward writes for this shape (warp-per-row kernels: 64 rows per CTA)
-static bool ln_warp_rows(int C) { return C <= 1024; }
+static bool ln_warp_rows(int C) { return C <= 1024; }        // backward (and its partial layout): up to 4 vectors per lane
+static bool ln_warp_rows_fwd(int C) { return C <= 2048; }    // forward: up to 8 vectors per lane (C = 2048: 1.5B model)
 extern "C" int vrwkv_ln_mix_blocks2(int rows, int C) {
     return ln_warp_rows(C) ? (rows + WR_RUN * WR_WARPS - 1) / (WR_RUN * WR_WARPS) : vrwkv_ln_mix_blocks(rows);
 }
@@ -948,9 +949,20 @@ extern "C" int vrwkv_ln_mix_forward(int rows, int T, int C, int nmix, float eps,
     a.h_out = h_out;
     a.stats = stats;
     if (nmix != 0 && nmix != 1 && nmix != 6) return vrwkv_fail(VRWKV_EUNSUP, "ln_mix_forward: nmix must be 0, 1 or 6");
-    if (ln_warp_rows(C)) {
-        const int nv = (C + 255) / 256, nblk = vrwkv_ln_mix_blocks2(rows, C);
-        VRWKV_WR(ln_mix_fwd_wr_kernel, nmix, nv, nblk, wr_smem(nmix, nv, false), (cudaStream_t)stream, a)
+    if (ln_warp_rows_fwd(C)) {
+        int nv = (C + 255) / 256;
+        nv = nv <= 4 ? nv : (nv <= 6 ? 6 : 8);
+        const int nblk = (rows + WR_RUN * WR_WARPS - 1) / (WR_RUN * WR_WARPS);
+        const size_t smem = wr_smem(nmix, nv, false);
+        if (nv <= 4) {
+            VRWKV_WR(ln_mix_fwd_wr_kernel, nmix, nv, nblk, smem, (cudaStream_t)stream, a)
+        } else {
+#define VRWKV_WR_BIG(nm)                                                                                        \
+    if (nv == 6) ln_mix_fwd_wr_kernel<nm, 6><<<nblk, WR_WARPS * 32, smem, (cudaStream_t)stream>>>(a);           \
+    else ln_mix_fwd_wr_kernel<nm, 8><<<nblk, WR_WARPS * 32, smem, (cudaStream_t)stream>>>(a);
+            if (nmix == 0) { VRWKV_WR_BIG(0) } else if (nmix == 1) { VRWKV_WR_BIG(1) } else { VRWKV_WR_BIG(6) }
+#undef VRWKV_WR_BIG
+        }
         VRWKV_CUDA(cudaGetLastError());
         vrwkv_count_launch(1);
         return VRWKV_OK;
