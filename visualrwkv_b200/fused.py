@@ -432,7 +432,7 @@ class CmixBlockFn(torch.autograd.Function):
 class HeadLossFn(torch.autograd.Function):
     """(features [B,T,C] after ln_out, head weight [V,C], labels [B,T]) -> scalar training loss.
 
-    logits = x W^T is one cuBLAS GEMM; the shifted CE (per-sample mean over valid labels, mean over the batch) and
+    logits = x W^T is one CTA-pair tcgen05 GEMM (gemm2); the shifted CE (per-sample mean over valid labels, mean over the batch) and
     the L2Wrap term are evaluated in ONE pass over the logits, and the backward overwrites the logits buffer with
     d(loss)/d(logits) in one more pass — instead of the ~10 passes over the 2.1 GB tensor the eager graph makes."""
 
