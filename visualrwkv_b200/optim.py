@@ -61,7 +61,10 @@ class FusedAdamW:
             t[:, 1] = np.array(ptrs, dtype=np.int64)
             t[:, 2] = np.array(self.offsets, dtype=np.int64)
             t[:, 3] = np.array([p.numel() for p in self.params], dtype=np.int64)
-            self._table.copy_(self._table_host, non_blocking=True)
+            # Outside a capture the upload blocks the host: the pinned staging table is rewritten by the next step that sees
+            # moved gradients, and an asynchronous copy still queued behind a slow GPU would then read the NEXT step's
+            # pointers.  Inside a capture the copy becomes a graph node (addresses are static from then on).
+            self._table.copy_(self._table_host, non_blocking=torch.cuda.is_current_stream_capturing())
             self._grad_ptrs = ptrs
 
     @torch.no_grad()
