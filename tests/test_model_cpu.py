@@ -167,3 +167,20 @@ def test_ddp_bucket_reducer_gloo_world2(tmp_path):
                           "127.0.0.1", "--master-port", "29533", str(script)], capture_output=True, text=True, env=env, timeout=240)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count("ok") == 2
+
+
+def test_wgrad_tiling_heuristic_and_model_bounds():
+    """Host logic only: when a weight gradient is left unsplit (the C library then tiles it 128 wide) and when the
+    contraction is sliced; the n_embd bound of the fused row kernels is enforced at construction."""
+    from visualrwkv_b200 import fused
+    from visualrwkv_b200.model import RWKV, default_args
+    rows = 16384
+    assert fused._ksplit(4, 768, 768, rows) == 1        # 36 tiles at N = 256 -> 72 tiles at N = 128: no split
+    assert fused._ksplit(2, 768, 3072, rows) == 2       # 72 tiles < 74 pairs and already >= 60: sliced once
+    assert fused._ksplit(1, 65536, 768, rows) == 1      # head weight gradient: 768 tiles
+    assert fused._ksplit(4, 768, 128, rows) > 1         # LoRA down-weight gradients: 12 tiles, sliced
+    assert fused._ksplit(4, 768, 128, 192) in (1, 2)    # never slices below whole k-blocks
+    assert fused.gemm2_supported(1, 768, 768) is False and fused.gemm2_supported(8, 768, 768) is True
+    import pytest
+    with pytest.raises(ValueError):
+        RWKV(default_args(n_embd=2560, n_layer=1, dim_att=2560))
